@@ -1,0 +1,224 @@
+/* ipxgpu.h -- C ABI of the B200-native IPX KKT-solve path (libipxgpu.so).
+ *
+ * Plain C types only: pointers, sizes, int64 indices (IPX's ipxint,
+ * reference include/ipx_config.h:5). No CUDA or torch types cross this
+ * boundary; device pointers are passed as void*.
+ *
+ * Each entry point replaces one interface of the reference (file:line cited
+ * per function). IPX has no FFI/plugin seam for this path; the reference-side
+ * binding is link-time substitution of six translation units, shown in
+ * INTEGRATION.md, whose replacements (ipx_b200/host/*.cc) call exactly these
+ * functions.
+ *
+ * Conventions
+ *  - every function returns 0 on success or an IPXGPU_ERR_* code and never
+ *    throws; ipxgpu_last_error() returns a thread-local message.
+ *  - "host" pointers are ordinary host memory owned by the caller; the context
+ *    copies. "_dev" entry points take device pointers on the context's device
+ *    and run asynchronously on the context's stream.
+ *  - there is NO CPU fallback: without a CUDA device ipxgpu_create fails.
+ */
+#ifndef IPXGPU_H_
+#define IPXGPU_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IPXGPU_OK 0
+#define IPXGPU_ERR_ARGUMENT 1
+#define IPXGPU_ERR_CUDA 2
+#define IPXGPU_ERR_OUT_OF_MEMORY 3
+#define IPXGPU_ERR_STATE 4
+#define IPXGPU_ERR_NCCL 5
+#define IPXGPU_ERR_UNSUPPORTED 6
+
+/* CR error flags, identical to reference include/ipx_status.h:31-35,47. */
+#define IPXGPU_CR_ITER_LIMIT 201
+#define IPXGPU_CR_MATRIX_NOT_POSDEF 202
+#define IPXGPU_CR_PRECOND_NOT_POSDEF 203
+#define IPXGPU_CR_NO_PROGRESS 204
+#define IPXGPU_CR_INF_OR_NAN 205
+
+typedef struct ipxgpu_ctx ipxgpu_ctx;
+
+typedef struct ipxgpu_options {
+    int32_t device;       /* CUDA ordinal; -1: env IPXGPU_DEVICE or current  */
+    int32_t rank;         /* column shard held by this context ...            */
+    int32_t nranks;       /* ... out of nranks (1 = whole matrix)             */
+    int64_t col_begin;    /* structural columns [col_begin, col_end) of this  */
+    int64_t col_end;      /* shard; -1/-1: split [0,n) evenly by nonzeros     */
+    int64_t panel_cols;   /* max columns per L2-resident panel; 0 = auto      */
+    void* stream;         /* cudaStream_t to run on; NULL: context-owned      */
+} ipxgpu_options;
+
+void ipxgpu_default_options(ipxgpu_options* opt);
+const char* ipxgpu_last_error(void);
+int ipxgpu_device_count(int* count);
+
+/* Creates a context for the solver-form matrix AI = [A I] (m rows, n+m
+ * columns, CSC, sorted row indices), i.e. Model::AI() (reference
+ * src/model.h:61). Uploads this shard's structural columns in CSC and CSR
+ * (int32 indices on device). Replaces the `const Model&` captured by the
+ * constructors of NormalMatrix / DiagonalPrecond / SplittedNormalMatrix
+ * (src/normal_matrix.cc:24, src/diagonal_precond.cc:12,
+ * src/splitted_normal_matrix.cc:11). */
+int ipxgpu_create(ipxgpu_ctx** ctx, int64_t m, int64_t n, const int64_t* AIp,
+                  const int64_t* AIi, const double* AIx,
+                  const ipxgpu_options* opt);
+void ipxgpu_destroy(ipxgpu_ctx* ctx);
+
+/* Dimensions and layout facts (for tests/benchmarks):
+ * out = [m, n, nnz_local, col_begin, col_end, num_panels, csc_tiles,
+ *        csr_tiles]. */
+int ipxgpu_get_layout(ipxgpu_ctx* ctx, int64_t out[8]);
+int ipxgpu_synchronize(ipxgpu_ctx* ctx);
+
+/* ---- multi-GPU: one context per rank, NCCL allreduce of the m-vector ---- */
+int ipxgpu_comm_unique_id(char id[128]);
+int ipxgpu_comm_init(ipxgpu_ctx* ctx, const char id[128]);
+
+/* ---- NormalMatrix (reference src/normal_matrix.h) ---- */
+
+/* NormalMatrix::Prepare (src/normal_matrix.cc:32-35). W: host, n+m entries, or
+ * NULL (W = 1 on structurals, 0 on slacks). The weights are copied to the
+ * device here (the reference captures the pointer; its only caller rebuilds W
+ * right before, src/kkt_solver_diag.cc:59). */
+int ipxgpu_normal_prepare(ipxgpu_ctx* ctx, const double* W);
+/* Same with W already on the device (full n+m vector; the shard reads its own
+ * columns). */
+int ipxgpu_normal_prepare_dev(ipxgpu_ctx* ctx, const void* W_dev);
+
+/* NormalMatrix::_Apply (src/normal_matrix.cc:45-126): lhs = AI*W*AI'*rhs,
+ * *rhs_dot_lhs = rhs'lhs if not NULL. Host vectors of m entries. With
+ * nranks > 1 the result is allreduced, every rank returns the full product. */
+int ipxgpu_normal_apply(ipxgpu_ctx* ctx, const double* rhs, double* lhs,
+                        double* rhs_dot_lhs);
+/* Device-resident variant: rhs_dev m doubles, lhs_dev m+1 doubles (entry m
+ * receives rhs'lhs). Asynchronous on the context's stream. */
+int ipxgpu_normal_apply_dev(ipxgpu_ctx* ctx, const void* rhs_dev,
+                            void* lhs_dev);
+
+/* ---- DiagonalPrecond (reference src/diagonal_precond.h) ---- */
+
+/* DiagonalPrecond::Factorize without dense columns
+ * (src/diagonal_precond.cc:28-46): diag = W[n:] + sum_j W[j]*a_ij^2.
+ * W: host n+m or NULL. use_prepared != 0: reuse the device weights of the last
+ * ipxgpu_normal_prepare (W is ignored). */
+int ipxgpu_diag_factorize(ipxgpu_ctx* ctx, const double* W, int use_prepared);
+int ipxgpu_diag_get(ipxgpu_ctx* ctx, double* diag);
+/* Installs a diagonal computed elsewhere (m host doubles). */
+int ipxgpu_diag_set(ipxgpu_ctx* ctx, const double* diag);
+/* DiagonalPrecond::_Apply (src/diagonal_precond.cc:150-157). */
+int ipxgpu_diag_apply(ipxgpu_ctx* ctx, const double* rhs, double* lhs,
+                      double* rhs_dot_lhs);
+
+/* ---- ConjugateResiduals (reference src/conjugate_residuals.h) ---- */
+
+typedef struct ipxgpu_cr_result {
+    int64_t errflag;   /* 0 or IPXGPU_CR_* / the interrupt callback's value */
+    int64_t iter;
+    double time;       /* host wall clock of the whole solve, seconds       */
+    double time_op;    /* device time in C.Apply (AAt, or NNt+B+Bt)         */
+    double time_pre;   /* device time in the kernels holding P.Apply         */
+    double time_B;     /* split operator only: L,U solves                   */
+    double time_Bt;    /* split operator only: U',L' solves                 */
+    double time_NNt;   /* split operator only: N N' product                 */
+    double resnorm;    /* last tested residual norm                         */
+} ipxgpu_cr_result;
+
+/* Polled between iteration batches; nonzero return aborts the solve and is
+ * returned as errflag (reference Control::InterruptCheck,
+ * src/conjugate_residuals.cc:84,209). May be NULL. */
+typedef int64_t (*ipxgpu_interrupt_fn)(void* user);
+
+/* ConjugateResiduals::Solve(C, P, rhs, tol, resscale, maxiter, lhs) with
+ * C = the prepared normal matrix, P = the factorized diagonal
+ * (src/conjugate_residuals.cc:90-213). lhs: initial iterate in, solution out.
+ * resscale may be NULL. maxiter < 0 => m+100. resnorm_hist (may be NULL)
+ * receives the residual norm tested at the top of each pass, up to hist_cap. */
+int ipxgpu_pcr_solve(ipxgpu_ctx* ctx, const double* rhs, double tol,
+                     const double* resscale, int64_t maxiter, double* lhs,
+                     ipxgpu_cr_result* result, ipxgpu_interrupt_fn interrupt,
+                     void* user, double* resnorm_hist, int64_t hist_cap);
+
+/* Same solve with every vector already on the device (m doubles each;
+ * resscale_dev may be NULL). zero_start != 0: lhs_dev is output only and the
+ * iteration starts from 0. No host<->device vector traffic. */
+int ipxgpu_pcr_solve_dev(ipxgpu_ctx* ctx, const void* rhs_dev, double tol,
+                         const void* resscale_dev, int64_t maxiter,
+                         void* lhs_dev, int zero_start,
+                         ipxgpu_cr_result* result);
+
+/* Unpreconditioned overload (src/conjugate_residuals.cc:14-88).
+ * op: 0 = normal matrix, 1 = split (basis-preconditioned) operator. */
+int ipxgpu_cr_solve(ipxgpu_ctx* ctx, int op, const double* rhs, double tol,
+                    const double* resscale, int64_t maxiter, double* lhs,
+                    ipxgpu_cr_result* result, ipxgpu_interrupt_fn interrupt,
+                    void* user, double* resnorm_hist, int64_t hist_cap);
+
+/* ---- KKTSolverDiag (reference src/kkt_solver_diag.cc) ---- */
+
+/* _Factorize (:18-65): builds W and resscale on the device from the iterate
+ * (xl,xu,zl,zu: host n+m each; all NULL => W = 1), prepares the normal matrix
+ * and the diagonal. W_out/resscale_out (host, may be NULL) receive copies. */
+int ipxgpu_kktdiag_factorize(ipxgpu_ctx* ctx, const double* xl,
+                             const double* xu, const double* zl,
+                             const double* zu, double mu, double* W_out,
+                             double* resscale_out);
+/* _Solve (:82-118): rhs = -b + AI*(W.*a), y = 0, PCR, recovery of x.
+ * a, x: host n+m; b, y: host m. */
+int ipxgpu_kktdiag_solve(ipxgpu_ctx* ctx, const double* a, const double* b,
+                         double tol, int64_t maxiter, double* x, double* y,
+                         ipxgpu_cr_result* result,
+                         ipxgpu_interrupt_fn interrupt, void* user);
+
+/* ---- sparse triangular solves (reference src/sparse_matrix.cc:224-311) ---- */
+
+/* Uploads L (strict lower, unit diagonal not stored) and U (upper, diagonal
+ * LAST in each column), both CSC dim x dim with sorted indices, builds their
+ * row-wise copies and the level schedules of the four solves. Replaces the
+ * factor export consumed by SplittedNormalMatrix::Prepare
+ * (src/splitted_normal_matrix.cc:26). out_levels (may be NULL) receives the
+ * level counts of [L, U, U', L'] solves. */
+int ipxgpu_lu_load(ipxgpu_ctx* ctx, int64_t dim, const int64_t* Lp,
+                   const int64_t* Li, const double* Lx, const int64_t* Up,
+                   const int64_t* Ui, const double* Ux, int64_t out_levels[4]);
+/* TriangularSolve on the loaded factors, in place on a host vector.
+ * which: 0 = L ('n', unit), 1 = U ('n'), 2 = U' ('t'), 3 = L' ('t', unit);
+ * 4 = ForwardSolve (L then U), 5 = BackwardSolve (U' then L'). */
+int ipxgpu_tri_solve(ipxgpu_ctx* ctx, int which, double* x);
+
+/* ---- SplittedNormalMatrix (reference src/splitted_normal_matrix.cc) ---- */
+
+/* Prepare (:18-66) after ipxgpu_lu_load. The U passed to ipxgpu_lu_load must
+ * already be column-scaled (:30-39). N = AI[:, NONBASIC] is formed on the
+ * device from the resident AI: nonbasic_scale holds colscale[j] for NONBASIC
+ * j and 0 for every other column (n+m host doubles, finite); rows are mapped
+ * through rowperm_inv (m host int64). free_positions: pivot positions of
+ * BASIC_FREE variables. */
+int ipxgpu_split_prepare(ipxgpu_ctx* ctx, const double* nonbasic_scale,
+                         const int64_t* rowperm_inv, int64_t num_free,
+                         const int64_t* free_positions);
+/* _Apply (:90-117). */
+int ipxgpu_split_apply(ipxgpu_ctx* ctx, const double* rhs, double* lhs,
+                       double* rhs_dot_lhs);
+
+/* ---- measurement helpers ---- */
+
+/* Runs `reps` device-resident normal-matrix applies on resident vectors and
+ * returns the mean device time per apply in ms (CUDA events on the context's
+ * stream), split into the two sweeps. flush_l2 != 0 writes a 256 MB buffer
+ * between repetitions (outside the timed intervals). out_ms = [apply, sweep1
+ * (A'x), sweep2 (A t)]. */
+int ipxgpu_time_normal_apply(ipxgpu_ctx* ctx, int reps, int flush_l2,
+                             double out_ms[3]);
+/* Number of kernels launched by this context since creation. */
+int ipxgpu_launch_count(ipxgpu_ctx* ctx, int64_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IPXGPU_H_ */

@@ -1,0 +1,161 @@
+// Host-side context of libipxgpu: device-resident matrix layouts, work
+// vectors and launch helpers.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "../../include/ipxgpu.h"
+
+namespace ipxgpu {
+
+extern thread_local std::string g_last_error;
+
+inline int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define IPXGPU_CUDA(call)                                                              \
+    do {                                                                               \
+        cudaError_t e_ = (call);                                                       \
+        if (e_ != cudaSuccess) {                                                       \
+            int code_ = (e_ == cudaErrorMemoryAllocation) ? IPXGPU_ERR_OUT_OF_MEMORY   \
+                                                          : IPXGPU_ERR_CUDA;           \
+            return fail(code_, std::string(#call) + ": " + cudaGetErrorString(e_));    \
+        }                                                                              \
+    } while (0)
+
+#define IPXGPU_TRY(call)              \
+    do {                              \
+        int rc_ = (call);             \
+        if (rc_ != IPXGPU_OK) return rc_; \
+    } while (0)
+
+// Device copy of a tiling of one compressed structure.
+struct TileSet {
+    Tile* tiles = nullptr;
+    int ntiles = 0;
+    int num_long = 0;
+    int* long_first = nullptr;
+    double* long_partials = nullptr;
+    unsigned* long_counters = nullptr;
+    LongInfo info() const { return LongInfo{long_first, long_partials, long_counters}; }
+};
+
+// Compressed structure on the device (CSC or CSR), int32 indices.
+struct DevMatrix {
+    int nseg = 0;
+    long long nnz = 0;
+    int* ptr = nullptr;
+    int* idx = nullptr;
+    double* val = nullptr;
+};
+
+// Column panel: columns [c0, c1) of the shard. The panel's slice of the
+// intermediate vector t (8*(c1-c0) bytes) is meant to stay in L2 between the
+// column sweep that writes it and the row sweep that gathers from it.
+struct Panel {
+    int c0 = 0, c1 = 0;
+    TileSet col_tiles;  // over columns [c0, c1) of the shard CSC
+    DevMatrix csr;      // rows of A[:, c0:c1], column ids local to the shard
+    TileSet row_tiles;
+};
+
+
+template <class T>
+inline int dev_alloc(T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    IPXGPU_CUDA(cudaMalloc((void**)p, count * sizeof(T)));
+    return IPXGPU_OK;
+}
+
+template <class T>
+inline void dev_free(T*& p) {
+    if (p) cudaFree((void*)p);
+    p = nullptr;
+}
+
+template <class T>
+inline int upload(T** dst, const std::vector<T>& src, cudaStream_t s) {
+    IPXGPU_TRY(dev_alloc(dst, src.size()));
+    if (!src.empty())
+        IPXGPU_CUDA(cudaMemcpyAsync(*dst, src.data(), src.size() * sizeof(T),
+                                    cudaMemcpyHostToDevice, s));
+    return IPXGPU_OK;
+}
+
+struct SplitOperator;  // split.cuh
+
+}  // namespace ipxgpu
+
+struct ipxgpu_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int64_t m = 0, n = 0;
+    int rank = 0, nranks = 1;
+    int64_t col_begin = 0, col_end = 0;
+    int nloc = 0;  // structural columns held by this shard
+    int64_t launches = 0;
+    int num_sms = 148;
+
+    ipxgpu::DevMatrix csc;  // shard's structural columns, rows global
+    std::vector<ipxgpu::Panel> panels;
+
+    // weights
+    double* W_own = nullptr;     // nloc + m owned copy: [structural shard | slack]
+    const double* Wc = nullptr;  // structural weights of the shard or nullptr (= 1)
+    const double* Ws = nullptr;  // slack weights or nullptr (= 0)
+    bool prepared = false;
+    double* W_full = nullptr;    // n+m, kktdiag path (nranks == 1 only)
+    double* resscale_kkt = nullptr;  // m
+    bool kkt_factorized = false;
+
+    double* t = nullptr;     // nloc
+    double* xin = nullptr;   // m
+    double* ybuf = nullptr;  // m+1
+    double* diag = nullptr;  // m
+    bool diag_ready = false;
+
+    // CR work vectors (allocated on first solve)
+    double *v_y = nullptr, *v_r = nullptr, *v_s = nullptr, *v_p = nullptr, *v_Cp = nullptr,
+           *v_Cs = nullptr, *v_q = nullptr, *v_rhs = nullptr, *v_resscale = nullptr,
+           *v_hist = nullptr;
+    int64_t hist_cap = 0;
+    double* nvec[3] = {nullptr, nullptr, nullptr};  // n+m scratch (kktdiag path)
+
+    ipxgpu::Reduce red{nullptr, nullptr};
+    int red_cap = 0;
+    ipxgpu::CrState* st_dev = nullptr;
+    ipxgpu::HostMirror* mirror_host = nullptr;
+    ipxgpu::HostMirror* mirror_dev = nullptr;
+    double* scalars = nullptr;  // small device scratch (8 doubles)
+
+    // NCCL (loaded on demand)
+    void* nccl_comm = nullptr;
+
+    // basis path
+    ipxgpu::SplitOperator* split = nullptr;
+
+    // L2 flush buffer for measurement helpers
+    char* flush_buf = nullptr;
+    size_t flush_bytes = 0;
+};
+
+namespace ipxgpu {
+inline int grid_for(const ipxgpu_ctx* c, long long n) {
+    long long g = (n + kBlock - 1) / kBlock;
+    const long long cap = (long long)c->num_sms * 8;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+}  // namespace ipxgpu

@@ -1,0 +1,1023 @@
+// libipxgpu: C ABI over the sm_100a kernels (see include/ipxgpu.h).
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdlib>
+#include <new>
+
+#include "context.cuh"
+#include "cr_kernels.cuh"
+#include "spmv_kernels.cuh"
+#include "split.cuh"
+
+namespace ipxgpu {
+
+thread_local std::string g_last_error;
+
+// ------------------------------------------------------------------ helpers
+
+// Cuts segments [seg_begin, seg_end) of a compressed structure into tiles.
+struct HostTiles {
+    std::vector<Tile> tiles;
+    std::vector<int> long_first;  // prefix over chunks, size num_long+1
+};
+
+template <class P>
+static HostTiles build_tiles(const P* ptr, int seg_begin, int seg_end, long long base) {
+    HostTiles out;
+    out.long_first.push_back(0);
+    int s = seg_begin;
+    while (s < seg_end) {
+        const long long p0 = ptr[s] - base;
+        const long long len = ptr[s + 1] - ptr[s];
+        if (len > kTileNnz) {
+            const int nch = (int)((len + kTileNnz - 1) / kTileNnz);
+            const int long_id = (int)out.long_first.size() - 1;
+            for (int c = 0; c < nch; c++) {
+                Tile t;
+                t.seg0 = s;
+                t.nseg = 1;
+                t.p0 = (int)(p0 + (long long)c * kTileNnz);
+                t.p1 = (int)std::min<long long>(p0 + len, p0 + (long long)(c + 1) * kTileNnz);
+                t.long_id = long_id;
+                t.chunk = c;
+                out.tiles.push_back(t);
+            }
+            out.long_first.push_back(out.long_first.back() + nch);
+            s++;
+            continue;
+        }
+        int e = s;
+        while (e < seg_end && e - s < kTileSeg && (ptr[e + 1] - base) - p0 <= kTileNnz &&
+               ptr[e + 1] - ptr[e] <= kTileNnz)
+            e++;
+        Tile t;
+        t.seg0 = s;
+        t.nseg = e - s;
+        t.p0 = (int)p0;
+        t.p1 = (int)(ptr[e] - base);
+        t.long_id = -1;
+        t.chunk = 0;
+        out.tiles.push_back(t);
+        s = e;
+    }
+    return out;
+}
+
+static int upload_tiles(TileSet* ts, const HostTiles& h, cudaStream_t s) {
+    ts->ntiles = (int)h.tiles.size();
+    ts->num_long = (int)h.long_first.size() - 1;
+    IPXGPU_TRY(upload(&ts->tiles, h.tiles, s));
+    IPXGPU_TRY(upload(&ts->long_first, h.long_first, s));
+    IPXGPU_TRY(dev_alloc(&ts->long_partials, (size_t)h.long_first.back()));
+    IPXGPU_TRY(dev_alloc(&ts->long_counters, (size_t)ts->num_long));
+    IPXGPU_CUDA(cudaMemsetAsync(ts->long_counters, 0,
+                                sizeof(unsigned) * std::max(1, ts->num_long), s));
+    return IPXGPU_OK;
+}
+
+static void free_tiles(TileSet* ts) {
+    dev_free(ts->tiles);
+    dev_free(ts->long_first);
+    dev_free(ts->long_partials);
+    dev_free(ts->long_counters);
+}
+
+static void free_matrix(DevMatrix* A) {
+    dev_free(A->ptr);
+    dev_free(A->idx);
+    dev_free(A->val);
+}
+
+static int ensure_reduce(ipxgpu_ctx* c, int grid) {
+    if (grid <= c->red_cap) return IPXGPU_OK;
+    IPXGPU_CUDA(cudaStreamSynchronize(c->stream));
+    dev_free(c->red.partials);
+    const int cap = std::max(grid, 4096);
+    IPXGPU_TRY(dev_alloc(&c->red.partials, (size_t)3 * cap));
+    if (!c->red.ticket) {
+        IPXGPU_TRY(dev_alloc(&c->red.ticket, 1));
+        IPXGPU_CUDA(cudaMemsetAsync(c->red.ticket, 0, sizeof(unsigned), c->stream));
+    }
+    c->red_cap = cap;
+    return IPXGPU_OK;
+}
+
+template <class Op>
+static int launch_sweep(ipxgpu_ctx* c, const Op& op, const TileSet& ts, const DevMatrix& A,
+                        CrState* st) {
+    if (ts.ntiles == 0) return IPXGPU_OK;
+    seg_sweep_kernel<Op><<<ts.ntiles, kBlock, 0, c->stream>>>(op, ts.tiles, A.ptr, A.idx, A.val,
+                                                              ts.info(), c->red, st);
+    c->launches++;
+    IPXGPU_CUDA(cudaGetLastError());
+    return IPXGPU_OK;
+}
+
+// ------------------------------------------------------------------ NCCL (dlopen)
+
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi* nccl_api() {
+    static NcclApi api;
+    if (api.handle) return &api;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return nullptr;
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+    api.AllReduce = (decltype(api.AllReduce))dlsym(h, "ncclAllReduce");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) return nullptr;
+    api.handle = h;
+    return &api;
+}
+
+static int allreduce_sum(ipxgpu_ctx* c, double* buf, size_t count) {
+    if (c->nranks == 1) return IPXGPU_OK;
+    if (!c->nccl_comm)
+        return fail(IPXGPU_ERR_STATE, "nranks > 1 but ipxgpu_comm_init was not called");
+    NcclApi* api = nccl_api();
+    ncclResult_t r = api->AllReduce(buf, buf, count, ncclDouble, ncclSum,
+                                    (ncclComm_t)c->nccl_comm, c->stream);
+    if (r != ncclSuccess)
+        return fail(IPXGPU_ERR_NCCL, std::string("ncclAllReduce: ") +
+                                         (api->GetErrorString ? api->GetErrorString(r) : "?"));
+    return IPXGPU_OK;
+}
+
+// ------------------------------------------------------------------ operator launches
+
+// lhs(m+1) = AI*W*AI'*x restricted to this shard (allreduced when sharded);
+// lhs[m] = x'lhs. `mode`/`slot`/`st` thread the CR scalar step through.
+static int launch_normal_apply_w(ipxgpu_ctx* c, const double* Wc, const double* Ws,
+                                 const double* x, double* y, int mode, int slot, CrState* st) {
+    const int np = (int)c->panels.size();
+    const bool sharded = c->nranks > 1;
+    if (np == 0 || c->m == 0) return IPXGPU_OK;
+    for (int k = 0; k < np; k++) {
+        const Panel& P = c->panels[k];
+        OpColDotScale op1{x, Wc, c->t};
+        IPXGPU_TRY(launch_sweep(c, op1, P.col_tiles, c->csc, st));
+        OpRowGather op2;
+        op2.t = c->t;
+        op2.x = x;
+        op2.Ws = (c->rank == 0) ? Ws : nullptr;
+        op2.y = y;
+        op2.m = (int)c->m;
+        op2.first_panel = (k == 0);
+        op2.last_panel = (k == np - 1);
+        op2.mode = sharded ? (int)kApplyPlain : mode;
+        op2.slot = slot;
+        IPXGPU_TRY(launch_sweep(c, op2, P.row_tiles, P.csr, sharded ? nullptr : st));
+    }
+    if (sharded) {
+        IPXGPU_TRY(allreduce_sum(c, y, (size_t)c->m + 1));
+        if (st && mode != kApplyPlain) {
+            cr_after_apply_kernel<<<1, 1, 0, c->stream>>>(y + c->m, mode, slot, st);
+            c->launches++;
+        }
+    }
+    return IPXGPU_OK;
+}
+
+static int launch_normal_apply(ipxgpu_ctx* c, const double* x, double* y, int mode, int slot,
+                               CrState* st) {
+    return launch_normal_apply_w(c, c->Wc, c->Ws, x, y, mode, slot, st);
+}
+
+static int launch_diag_build(ipxgpu_ctx* c, const double* Wc, const double* Ws) {
+    const int np = (int)c->panels.size();
+    for (int k = 0; k < np; k++) {
+        const Panel& P = c->panels[k];
+        OpRowDiag op{Wc, (c->rank == 0) ? Ws : nullptr, c->diag, k == 0};
+        IPXGPU_TRY(launch_sweep(c, op, P.row_tiles, P.csr, nullptr));
+    }
+    IPXGPU_TRY(allreduce_sum(c, c->diag, (size_t)c->m));
+    c->diag_ready = true;
+    return IPXGPU_OK;
+}
+
+static int launch_operator(ipxgpu_ctx* c, int op, const double* x, double* y, int mode,
+                           CrState* st) {
+    if (op == 0) return launch_normal_apply(c, x, y, mode, kSlotOp, st);
+    return launch_split_apply(c, x, y, mode, st);
+}
+
+// ------------------------------------------------------------------ buffers
+
+static int ensure_cr_buffers(ipxgpu_ctx* c, int64_t hist_cap) {
+    const size_t m = (size_t)c->m;
+    if (!c->v_y) {
+        IPXGPU_TRY(dev_alloc(&c->v_y, m));
+        IPXGPU_TRY(dev_alloc(&c->v_r, m));
+        IPXGPU_TRY(dev_alloc(&c->v_s, m));
+        IPXGPU_TRY(dev_alloc(&c->v_p, m));
+        IPXGPU_TRY(dev_alloc(&c->v_Cp, m));
+        IPXGPU_TRY(dev_alloc(&c->v_Cs, m + 1));
+        IPXGPU_TRY(dev_alloc(&c->v_q, m));
+        IPXGPU_TRY(dev_alloc(&c->v_rhs, m));
+        IPXGPU_TRY(dev_alloc(&c->v_resscale, m));
+    }
+    if (hist_cap > c->hist_cap) {
+        dev_free(c->v_hist);
+        IPXGPU_TRY(dev_alloc(&c->v_hist, (size_t)hist_cap));
+        c->hist_cap = hist_cap;
+    }
+    return IPXGPU_OK;
+}
+
+static int ensure_nvecs(ipxgpu_ctx* c) {
+    for (int k = 0; k < 3; k++)
+        if (!c->nvec[k]) IPXGPU_TRY(dev_alloc(&c->nvec[k], (size_t)(c->n + c->m)));
+    return IPXGPU_OK;
+}
+
+__global__ void cr_start_kernel(CrState* st) { st->t_last = globaltimer(); }
+
+static inline void cpu_relax() {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+}
+
+// Device-resident CR driver. Vectors v_rhs, v_y (initial iterate, only if
+// !zero_start), v_resscale (if use_resscale) must be on the device already.
+static int run_cr(ipxgpu_ctx* c, int op, bool precond, bool zero_start, bool use_resscale,
+                  double tol, int64_t maxiter, ipxgpu_cr_result* result,
+                  ipxgpu_interrupt_fn interrupt, void* user, int64_t hist_cap) {
+    const int m = (int)c->m;
+    if (maxiter < 0) maxiter = c->m + 100;
+    const int grid = grid_for(c, m);
+    IPXGPU_TRY(ensure_reduce(c, grid));
+
+    CrState h;
+    std::memset(&h, 0, sizeof h);
+    h.tol = tol;
+    h.maxiter = maxiter;
+    h.precond = precond ? 1 : 0;
+    h.hist = hist_cap > 0 ? c->v_hist : nullptr;
+    h.hist_cap = hist_cap;
+    h.mirror = c->mirror_dev;
+    c->mirror_host->iter = 0;
+    c->mirror_host->done = 0;
+    c->mirror_host->errflag = 0;
+    c->mirror_host->resnorm = 0.0;
+    IPXGPU_CUDA(cudaMemcpyAsync(c->st_dev, &h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+    cr_start_kernel<<<1, 1, 0, c->stream>>>(c->st_dev);
+    c->launches++;
+
+    CrVectors v;
+    v.m = m;
+    v.y = c->v_y;
+    v.r = c->v_r;
+    v.s = c->v_s;
+    v.p = c->v_p;
+    v.Cp = c->v_Cp;
+    v.Cs = c->v_Cs;
+    v.q = c->v_q;
+    v.diag = c->diag;
+    v.resscale = use_resscale ? c->v_resscale : nullptr;
+    CrState* st = c->st_dev;
+
+    if (m == 0) {
+        if (result) std::memset(result, 0, sizeof *result);
+        return IPXGPU_OK;
+    }
+
+    // Initialisation (reference src/conjugate_residuals.cc:33-40, :118-127).
+    if (zero_start) {
+        IPXGPU_CUDA(cudaMemsetAsync(c->v_y, 0, sizeof(double) * m, c->stream));
+        cr_init_kernel<<<grid, kBlock, 0, c->stream>>>(v, c->v_rhs, nullptr, c->red, st);
+    } else {
+        IPXGPU_TRY(launch_operator(c, op, c->v_y, c->v_Cs, kApplyPlain, nullptr));
+        cr_init_kernel<<<grid, kBlock, 0, c->stream>>>(v, c->v_rhs, c->v_Cs, c->red, st);
+    }
+    c->launches++;
+    IPXGPU_TRY(launch_operator(c, op, precond ? c->v_s : c->v_r, c->v_Cs, kApplyCrInit, st));
+    cr_direction_kernel<<<grid, kBlock, 0, c->stream>>>(v, c->red, st);
+    c->launches++;
+    IPXGPU_CUDA(cudaGetLastError());
+
+    auto enqueue_pass = [&]() -> int {
+        cr_update_kernel<<<grid, kBlock, 0, c->stream>>>(v, c->red, st);
+        c->launches++;
+        IPXGPU_TRY(launch_operator(c, op, precond ? c->v_s : c->v_r, c->v_Cs, kApplyCrIter, st));
+        cr_direction_kernel<<<grid, kBlock, 0, c->stream>>>(v, c->red, st);
+        c->launches++;
+        return IPXGPU_OK;
+    };
+
+    const int kBatch = 8;
+    long long enqueued = 0;
+    int64_t interrupted = 0;
+    volatile HostMirror* mir = c->mirror_host;
+    if (c->nranks > 1) {
+        // All ranks must issue the same collectives: advance in lock step.
+        for (;;) {
+            IPXGPU_CUDA(cudaStreamSynchronize(c->stream));
+            if (mir->done) break;
+            if (interrupt && (interrupted = interrupt(user)) != 0) break;
+            for (int b = 0; b < kBatch; b++) IPXGPU_TRY(enqueue_pass());
+        }
+    } else {
+        unsigned long long polls = 0;
+        for (;;) {
+            if (mir->done) break;
+            if (enqueued - mir->iter <= kBatch) {
+                if (interrupt && (interrupted = interrupt(user)) != 0) break;
+                for (int b = 0; b < kBatch; b++) IPXGPU_TRY(enqueue_pass());
+                enqueued += kBatch;
+                IPXGPU_CUDA(cudaGetLastError());
+                continue;
+            }
+            if ((++polls & 0xfff) == 0) {
+                cudaError_t q = cudaStreamQuery(c->stream);
+                if (q != cudaSuccess && q != cudaErrorNotReady)
+                    return fail(IPXGPU_ERR_CUDA, std::string("CR loop: ") + cudaGetErrorString(q));
+                if (q == cudaSuccess && !mir->done && enqueued - mir->iter > kBatch)
+                    return fail(IPXGPU_ERR_STATE, "CR loop stalled: stream idle but not done");
+            }
+            cpu_relax();
+        }
+    }
+    IPXGPU_CUDA(cudaStreamSynchronize(c->stream));
+    IPXGPU_CUDA(cudaMemcpy(&h, c->st_dev, sizeof h, cudaMemcpyDeviceToHost));
+    if (result) {
+        result->errflag = interrupted ? interrupted : h.errflag;
+        result->iter = h.iter;
+        result->time_op = 1e-9 * (double)h.t_op;
+        result->time_pre = 1e-9 * (double)h.t_pre;
+        result->time_B = 1e-9 * (double)h.t_B;
+        result->time_Bt = 1e-9 * (double)h.t_Bt;
+        result->time_NNt = 1e-9 * (double)h.t_NNt;
+        if (op == 1) result->time_op = result->time_B + result->time_Bt + result->time_NNt;
+        result->resnorm = h.resnorm;
+    }
+    return IPXGPU_OK;
+}
+
+static int check_ctx(const ipxgpu_ctx* c) {
+    if (!c) return fail(IPXGPU_ERR_ARGUMENT, "null context");
+    cudaError_t e = cudaSetDevice(c->device);
+    if (e != cudaSuccess) return fail(IPXGPU_ERR_CUDA, cudaGetErrorString(e));
+    return IPXGPU_OK;
+}
+
+}  // namespace ipxgpu
+
+using namespace ipxgpu;
+
+// =================================================================== C ABI
+
+extern "C" {
+
+void ipxgpu_default_options(ipxgpu_options* opt) {
+    if (!opt) return;
+    opt->device = -1;
+    opt->rank = 0;
+    opt->nranks = 1;
+    opt->col_begin = -1;
+    opt->col_end = -1;
+    opt->panel_cols = 0;
+    opt->stream = nullptr;
+}
+
+const char* ipxgpu_last_error(void) { return g_last_error.c_str(); }
+
+int ipxgpu_device_count(int* count) {
+    if (!count) return fail(IPXGPU_ERR_ARGUMENT, "null count");
+    *count = 0;
+    IPXGPU_CUDA(cudaGetDeviceCount(count));
+    return IPXGPU_OK;
+}
+
+void ipxgpu_destroy(ipxgpu_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    destroy_split(c);
+    free_matrix(&c->csc);
+    for (Panel& P : c->panels) {
+        free_tiles(&P.col_tiles);
+        free_tiles(&P.row_tiles);
+        free_matrix(&P.csr);
+    }
+    dev_free(c->W_own);
+    dev_free(c->W_full);
+    dev_free(c->resscale_kkt);
+    dev_free(c->t);
+    dev_free(c->xin);
+    dev_free(c->ybuf);
+    dev_free(c->diag);
+    dev_free(c->v_y); dev_free(c->v_r); dev_free(c->v_s); dev_free(c->v_p); dev_free(c->v_Cp);
+    dev_free(c->v_Cs); dev_free(c->v_q); dev_free(c->v_rhs); dev_free(c->v_resscale);
+    dev_free(c->v_hist);
+    for (int k = 0; k < 3; k++) dev_free(c->nvec[k]);
+    dev_free(c->red.partials);
+    dev_free(c->red.ticket);
+    dev_free(c->st_dev);
+    dev_free(c->scalars);
+    dev_free(c->flush_buf);
+    if (c->mirror_host) cudaFreeHost(c->mirror_host);
+    if (c->nccl_comm) {
+        NcclApi* api = nccl_api();
+        if (api) api->CommDestroy((ncclComm_t)c->nccl_comm);
+    }
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int ipxgpu_create(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp, const int64_t* AIi,
+                  const double* AIx, const ipxgpu_options* opt_in) {
+    if (!out) return fail(IPXGPU_ERR_ARGUMENT, "null ctx out");
+    *out = nullptr;
+    if (m < 0 || n < 0 || !AIp || (AIp[n] > 0 && (!AIi || !AIx)))
+        return fail(IPXGPU_ERR_ARGUMENT, "invalid matrix arguments");
+    ipxgpu_options opt;
+    ipxgpu_default_options(&opt);
+    if (opt_in) opt = *opt_in;
+    if (opt.nranks < 1 || opt.rank < 0 || opt.rank >= opt.nranks)
+        return fail(IPXGPU_ERR_ARGUMENT, "invalid rank/nranks");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(IPXGPU_ERR_CUDA, std::string("no CUDA device (libipxgpu has no CPU path): ") +
+                                         cudaGetErrorString(e));
+    int device = opt.device;
+    if (device < 0) {
+        const char* env = std::getenv("IPXGPU_DEVICE");
+        if (env) device = std::atoi(env);
+        else IPXGPU_CUDA(cudaGetDevice(&device));
+    }
+    if (device >= ndev) return fail(IPXGPU_ERR_ARGUMENT, "device ordinal out of range");
+    IPXGPU_CUDA(cudaSetDevice(device));
+
+    ipxgpu_ctx* c = new (std::nothrow) ipxgpu_ctx;
+    if (!c) return fail(IPXGPU_ERR_OUT_OF_MEMORY, "host allocation failed");
+    struct Guard {
+        ipxgpu_ctx* c;
+        ~Guard() { if (c) ipxgpu_destroy(c); }
+    } guard{c};
+
+    c->device = device;
+    c->m = m;
+    c->n = n;
+    c->rank = opt.rank;
+    c->nranks = opt.nranks;
+    cudaDeviceProp prop;
+    IPXGPU_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->num_sms = prop.multiProcessorCount;
+    if (opt.stream) {
+        c->stream = (cudaStream_t)opt.stream;
+    } else {
+        IPXGPU_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+
+    // Column shard: explicit, or balanced by nonzeros.
+    int64_t cb = opt.col_begin, ce = opt.col_end;
+    if (cb < 0 || ce < 0) {
+        const int64_t nnzA = AIp[n];
+        auto cut = [&](int r) -> int64_t {
+            if (r <= 0) return 0;
+            if (r >= opt.nranks) return n;
+            const int64_t target = nnzA / opt.nranks * r;
+            return std::lower_bound(AIp, AIp + n + 1, target) - AIp;
+        };
+        cb = cut(opt.rank);
+        ce = cut(opt.rank + 1);
+    }
+    if (cb < 0 || ce < cb || ce > n) return fail(IPXGPU_ERR_ARGUMENT, "invalid column range");
+    c->col_begin = cb;
+    c->col_end = ce;
+    const int64_t nloc = ce - cb;
+    const int64_t base = AIp[cb];
+    const int64_t nnz = AIp[ce] - base;
+    if (nnz >= (int64_t)INT32_MAX || nloc >= (int64_t)INT32_MAX || m >= (int64_t)INT32_MAX)
+        return fail(IPXGPU_ERR_UNSUPPORTED, "shard exceeds int32 index range; use more shards");
+    c->nloc = (int)nloc;
+    c->csc.nseg = (int)nloc;
+    c->csc.nnz = nnz;
+
+    cudaStream_t s = c->stream;
+    try {
+        // Shard CSC with int32 indices.
+        std::vector<int> cp(nloc + 1), ci((size_t)nnz);
+        for (int64_t j = 0; j <= nloc; j++) cp[j] = (int)(AIp[cb + j] - base);
+        for (int64_t p = 0; p < nnz; p++) {
+            const int64_t i = AIi[base + p];
+            if (i < 0 || i >= m) return fail(IPXGPU_ERR_ARGUMENT, "row index out of range");
+            ci[p] = (int)i;
+        }
+        IPXGPU_TRY(upload(&c->csc.ptr, cp, s));
+        IPXGPU_TRY(upload(&c->csc.idx, ci, s));
+        IPXGPU_TRY(dev_alloc(&c->csc.val, (size_t)nnz));
+        if (nnz > 0)
+            IPXGPU_CUDA(cudaMemcpyAsync(c->csc.val, AIx + base, sizeof(double) * nnz,
+                                        cudaMemcpyHostToDevice, s));
+
+        // Panels: t-slice of at most panel_cols columns (default 2M = 16 MB).
+        int64_t pc = opt.panel_cols > 0 ? opt.panel_cols : (int64_t)2 << 20;
+        const char* env_pc = std::getenv("IPXGPU_PANEL_COLS");
+        if (opt.panel_cols <= 0 && env_pc) pc = std::max<int64_t>(1, std::atoll(env_pc));
+        const int npanels = (int)std::max<int64_t>(1, (nloc + pc - 1) / pc);
+        c->panels.resize(nloc > 0 ? npanels : 0);
+        int max_grid = 1;
+        for (int k = 0; k < (int)c->panels.size(); k++) {
+            Panel& P = c->panels[k];
+            P.c0 = (int)(nloc * k / npanels);
+            P.c1 = (int)(nloc * (k + 1) / npanels);
+            HostTiles ct = build_tiles(cp.data(), P.c0, P.c1, 0);
+            IPXGPU_TRY(upload_tiles(&P.col_tiles, ct, s));
+            // CSR of the panel (rows global, columns local to the shard,
+            // ascending within a row).
+            const int64_t q0 = cp[P.c0], q1 = cp[P.c1];
+            std::vector<int> rp((size_t)m + 1, 0);
+            for (int64_t p = q0; p < q1; p++) rp[ci[p] + 1]++;
+            for (int64_t i = 0; i < m; i++) rp[i + 1] += rp[i];
+            std::vector<int> rj((size_t)(q1 - q0));
+            std::vector<double> rx((size_t)(q1 - q0));
+            {
+                std::vector<int> next(rp.begin(), rp.end() - 1);
+                for (int j = P.c0; j < P.c1; j++)
+                    for (int p = cp[j]; p < cp[j + 1]; p++) {
+                        const int put = next[ci[p]]++;
+                        rj[put] = j;
+                        rx[put] = AIx[base + p];
+                    }
+            }
+            P.csr.nseg = (int)m;
+            P.csr.nnz = q1 - q0;
+            IPXGPU_TRY(upload(&P.csr.ptr, rp, s));
+            IPXGPU_TRY(upload(&P.csr.idx, rj, s));
+            IPXGPU_TRY(upload(&P.csr.val, rx, s));
+            HostTiles rt = build_tiles(rp.data(), 0, (int)m, 0);
+            IPXGPU_TRY(upload_tiles(&P.row_tiles, rt, s));
+            max_grid = std::max(max_grid, std::max(P.col_tiles.ntiles, P.row_tiles.ntiles));
+            IPXGPU_CUDA(cudaStreamSynchronize(s));  // host vectors die here
+        }
+        IPXGPU_TRY(dev_alloc(&c->t, (size_t)nloc));
+        IPXGPU_TRY(dev_alloc(&c->xin, (size_t)m));
+        IPXGPU_TRY(dev_alloc(&c->ybuf, (size_t)m + 1));
+        IPXGPU_TRY(dev_alloc(&c->diag, (size_t)m));
+        IPXGPU_TRY(dev_alloc(&c->W_own, (size_t)(nloc + m)));
+        IPXGPU_TRY(dev_alloc(&c->st_dev, 1));
+        IPXGPU_TRY(dev_alloc(&c->scalars, 8));
+        IPXGPU_TRY(ensure_reduce(c, std::max(max_grid, c->num_sms * 8)));
+        IPXGPU_CUDA(cudaHostAlloc((void**)&c->mirror_host, sizeof(HostMirror),
+                                  cudaHostAllocMapped));
+        std::memset(c->mirror_host, 0, sizeof(HostMirror));
+        IPXGPU_CUDA(cudaHostGetDevicePointer((void**)&c->mirror_dev, c->mirror_host, 0));
+        IPXGPU_CUDA(cudaStreamSynchronize(s));
+    } catch (const std::bad_alloc&) {
+        return fail(IPXGPU_ERR_OUT_OF_MEMORY, "host allocation failed while building layouts");
+    }
+    guard.c = nullptr;
+    *out = c;
+    return IPXGPU_OK;
+}
+
+int ipxgpu_get_layout(ipxgpu_ctx* c, int64_t out[8]) {
+    if (!c || !out) return fail(IPXGPU_ERR_ARGUMENT, "null argument");
+    int64_t ct = 0, rt = 0;
+    for (const Panel& P : c->panels) {
+        ct += P.col_tiles.ntiles;
+        rt += P.row_tiles.ntiles;
+    }
+    out[0] = c->m; out[1] = c->n; out[2] = c->csc.nnz; out[3] = c->col_begin;
+    out[4] = c->col_end; out[5] = (int64_t)c->panels.size(); out[6] = ct; out[7] = rt;
+    return IPXGPU_OK;
+}
+
+int ipxgpu_synchronize(ipxgpu_ctx* c) {
+    IPXGPU_TRY(check_ctx(c));
+    IPXGPU_CUDA(cudaStreamSynchronize(c->stream));
+    return IPXGPU_OK;
+}
+
+int ipxgpu_launch_count(ipxgpu_ctx* c, int64_t* count) {
+    if (!c || !count) return fail(IPXGPU_ERR_ARGUMENT, "null argument");
+    *count = c->launches;
+    return IPXGPU_OK;
+}
+
+// ---- NCCL ----
+
+int ipxgpu_comm_unique_id(char id[128]) {
+    NcclApi* api = nccl_api();
+    if (!api) return fail(IPXGPU_ERR_NCCL, "libnccl.so.2 not found");
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId uid;
+    ncclResult_t r = api->GetUniqueId(&uid);
+    if (r != ncclSuccess) return fail(IPXGPU_ERR_NCCL, "ncclGetUniqueId failed");
+    std::memcpy(id, &uid, 128);
+    return IPXGPU_OK;
+}
+
+int ipxgpu_comm_init(ipxgpu_ctx* c, const char id[128]) {
+    IPXGPU_TRY(check_ctx(c));
+    NcclApi* api = nccl_api();
+    if (!api) return fail(IPXGPU_ERR_NCCL, "libnccl.so.2 not found");
+    ncclUniqueId uid;
+    std::memcpy(&uid, id, 128);
+    ncclComm_t comm;
+    ncclResult_t r = api->CommInitRank(&comm, c->nranks, uid, c->rank);
+    if (r != ncclSuccess)
+        return fail(IPXGPU_ERR_NCCL, std::string("ncclCommInitRank: ") +
+                                         (api->GetErrorString ? api->GetErrorString(r) : "?"));
+    c->nccl_comm = comm;
+    return IPXGPU_OK;
+}
+
+// ---- NormalMatrix ----
+
+int ipxgpu_normal_prepare(ipxgpu_ctx* c, const double* W) {
+    IPXGPU_TRY(check_ctx(c));
+    if (W) {
+        IPXGPU_CUDA(cudaMemcpyAsync(c->W_own, W + c->col_begin, sizeof(double) * c->nloc,
+                                    cudaMemcpyHostToDevice, c->stream));
+        IPXGPU_CUDA(cudaMemcpyAsync(c->W_own + c->nloc, W + c->n, sizeof(double) * c->m,
+                                    cudaMemcpyHostToDevice, c->stream));
+        IPXGPU_CUDA(cudaStreamSynchronize(c->stream));
+        c->Wc = c->W_own;
+        c->Ws = c->W_own + c->nloc;
+    } else {
+        c->Wc = nullptr;
+        c->Ws = nullptr;
+    }
+    c->prepared = true;
+    return IPXGPU_OK;
+}
+
+int ipxgpu_normal_prepare_dev(ipxgpu_ctx* c, const void* W_dev) {
+    IPXGPU_TRY(check_ctx(c));
+    const double* W = (const double*)W_dev;
+    c->Wc = W ? W + c->col_begin : nullptr;
+    c->Ws = W ? W + c->n : nullptr;
+    c->prepared = true;
+    return IPXGPU_OK;
+}
+
+int ipxgpu_normal_apply_dev(ipxgpu_ctx* c, const void* rhs_dev, void* lhs_dev) {
+    IPXGPU_TRY(check_ctx(c));
+    if (!c->prepared) return fail(IPXGPU_ERR_STATE, "normal matrix not prepared");
+    return launch_normal_apply(c, (const double*)rhs_dev, (double*)lhs_dev, kApplyPlain,
+                               kSlotNone, nullptr);
+}
+
+int ipxgpu_normal_apply(ipxgpu_ctx* c, const double* rhs, double* lhs, double* rhs_dot_lhs) {
+    IPXGPU_TRY(check_ctx(c));
+    if (!c->prepared) return fail(IPXGPU_ERR_STATE, "normal matrix not prepared");
+    if (!rhs || !lhs) return fail(IPXGPU_ERR_ARGUMENT, "null vector");
+    const size_t m = (size_t)c->m;
+    IPXGPU_CUDA(cudaMemcpyAsync(c->xin, rhs, sizeof(double) * m, cudaMemcpyHostToDevice,
+                                c->stream));
+    IPXGPU_TRY(launch_normal_apply(c, c->xin, c->ybuf, kApplyPlain, kSlotNone, nullptr));
+    IPXGPU_CUDA(cudaMemcpyAsync(lhs, c->ybuf, sizeof(double) * m, cudaMemcpyDeviceToHost,
+                                c->stream));
+    double dot = 0.0;
+    if (rhs_dot_lhs && m > 0)
+        IPXGPU_CUDA(cudaMemcpyAsync(&dot, c->ybuf + m, sizeof(double), cudaMemcpyDeviceToHost,
+                                    c->stream));
+    IPXGPU_CUDA(cudaStreamSynchronize(c->stream));
+    if (rhs_dot_lhs) *rhs_dot_lhs = dot;
+    return IPXGPU_OK;
+}
+
+// ---- DiagonalPrecond ----
+
+int ipxgpu_diag_factorize(ipxgpu_ctx* c, const double* W, int use_prepared) {
+    IPXGPU_TRY(check_ctx(c));
+    const double *Wc, *Ws;
+    if (use_prepared) {
+        if (!c->prepared) return fail(IPXGPU_ERR_STATE, "normal matrix not prepared");
+        Wc = c->Wc;
+        Ws = c->Ws;
+    } else if (W) {
+        // Stage into the tail of the n-vector scratch so the prepared weights
+        // of the normal matrix stay intact.
+        IPXGPU_TRY(ensure_nvecs(c));
+        double* stage = c->nvec[0];
+        IPXGPU_CUDA(cudaMemcpyAsync(stage, W + c->col_begin, sizeof(double) * c->nloc,
+                                    cudaMemcpyHostToDevice, c->stream));
+        IPXGPU_CUDA(cudaMemcpyAsync(stage + c->nloc, W + c->n, sizeof(double) * c->m,
+                                    cudaMemcpyHostToDevice, c->stream));
+        Wc = stage;
+        Ws = stage + c->nloc;
+    } else {
+        Wc = nullptr;
+        Ws = nullptr;
+    }
+    if (c->panels.empty())
+        IPXGPU_CUDA(cudaMemsetAsync(c->diag, 0, sizeof(double) * std::max<int64_t>(1, c->m),
+                                    c->stream));
+    IPXGPU_TRY(launch_diag_build(c, Wc, Ws));
+    IPXGPU_CUDA(cudaStreamSynchronize(c->stream));
+    return IPXGPU_OK;
+}
+
+int ipxgpu_diag_get(ipxgpu_ctx* c, double* diag) {
+    IPXGPU_TRY(check_ctx(c));
+    if (!c->diag_ready) return fail(IPXGPU_ERR_STATE, "diagonal not factorized");
+    IPXGPU_CUDA(cudaMemcpyAsync(diag, c->diag, sizeof(double) * c->m, cudaMemcpyDeviceToHost,
+                                c->stream));
+    IPXGPU_CUDA(cudaStreamSynchronize(c->stream));
+    return IPXGPU_OK;
+}
+
+int ipxgpu_diag_set(ipxgpu_ctx* c, const double* diag) {
+    IPXGPU_TRY(check_ctx(c));
+    IPXGPU_CUDA(cudaMemcpyAsync(c->diag, diag, sizeof(double) * c->m, cudaMemcpyHostToDevice,
+                                c->stream));
+    IPXGPU_CUDA(cudaStreamSynchronize(c->stream));
+    c->diag_ready = true;
+    return IPXGPU_OK;
+}
+
+int ipxgpu_diag_apply(ipxgpu_ctx* c, const double* rhs, double* lhs, double* rhs_dot_lhs) {
+    IPXGPU_TRY(check_ctx(c));
+    if (!c->diag_ready) return fail(IPXGPU_ERR_STATE, "diagonal not factorized");
+    const int m = (int)c->m;
+    const int grid = grid_for(c, m);
+    IPXGPU_TRY(ensure_reduce(c, grid));
+    IPXGPU_CUDA(cudaMemcpyAsync(c->xin, rhs, sizeof(double) * m, cudaMemcpyHostToDevice,
+                                c->stream));
+    diag_apply_kernel<<<grid, kBlock, 0, c->stream>>>(m, c->diag, c->xin, c->ybuf, c->red,
+                                                      c->ybuf + m);
+    c->launches++;
+    IPXGPU_CUDA(cudaGetLastError());
+    IPXGPU_CUDA(cudaMemcpyAsync(lhs, c->ybuf, sizeof(double) * m, cudaMemcpyDeviceToHost,
+                                c->stream));
+    double dot = 0.0;
+    IPXGPU_CUDA(cudaMemcpyAsync(&dot, c->ybuf + m, sizeof(double), cudaMemcpyDeviceToHost,
+                                c->stream));
+    IPXGPU_CUDA(cudaStreamSynchronize(c->stream));
+    if (rhs_dot_lhs) *rhs_dot_lhs = dot;
+    return IPXGPU_OK;
+}
+
+// ---- ConjugateResiduals ----
+
+static int cr_host_entry(ipxgpu_ctx* c, int op, bool precond, const double* rhs, double tol,
+                         const double* resscale, int64_t maxiter, double* lhs,
+                         ipxgpu_cr_result* result, ipxgpu_interrupt_fn interrupt, void* user,
+                         double* hist, int64_t hist_cap) {
+    IPXGPU_TRY(check_ctx(c));
+    if (!rhs || !lhs) return fail(IPXGPU_ERR_ARGUMENT, "null vector");
+    if (op == 0 && !c->prepared) return fail(IPXGPU_ERR_STATE, "normal matrix not prepared");
+    if (op == 1 && !split_ready(c)) return fail(IPXGPU_ERR_STATE, "split operator not prepared");
+    if (op != 0 && op != 1) return fail(IPXGPU_ERR_ARGUMENT, "unknown operator");
+    if (precond && !c->diag_ready) return fail(IPXGPU_ERR_STATE, "diagonal not factorized");
+    const auto t0 = std::chrono::steady_clock::now();
+    if (!hist) hist_cap = 0;
+    IPXGPU_TRY(ensure_cr_buffers(c, hist_cap));
+    const size_t m = (size_t)c->m;
+    // Infnorm(lhs) == 0 saves a matrix-vector product
+    // (reference src/conjugate_residuals.cc:33, :118).
+    bool zero_start = true;
+    for (size_t i = 0; i < m; i++)
+        if (std::fabs(lhs[i]) > 0.0 || lhs[i] != lhs[i]) { zero_start = false; break; }
+    IPXGPU_CUDA(cudaMemcpyAsync(c->v_rhs, rhs, sizeof(double) * m, cudaMemcpyHostToDevice,
+                                c->stream));
+    if (!zero_start)
+        IPXGPU_CUDA(cudaMemcpyAsync(c->v_y, lhs, sizeof(double) * m, cudaMemcpyHostToDevice,
+                                    c->stream));
+    if (resscale)
+        IPXGPU_CUDA(cudaMemcpyAsync(c->v_resscale, resscale, sizeof(double) * m,
+                                    cudaMemcpyHostToDevice, c->stream));
+    if (hist_cap > 0)
+        IPXGPU_CUDA(cudaMemsetAsync(c->v_hist, 0xff, sizeof(double) * hist_cap, c->stream));
+    IPXGPU_TRY(run_cr(c, op, precond, zero_start, resscale != nullptr, tol, maxiter, result,
+                      interrupt, user, hist_cap));
+    IPXGPU_CUDA(cudaMemcpy(lhs, c->v_y, sizeof(double) * m, cudaMemcpyDeviceToHost));
+    if (hist_cap > 0)
+        IPXGPU_CUDA(cudaMemcpy(hist, c->v_hist, sizeof(double) * hist_cap,
+                               cudaMemcpyDeviceToHost));
+    if (result)
+        result->time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return IPXGPU_OK;
+}
+
+int ipxgpu_pcr_solve(ipxgpu_ctx* c, const double* rhs, double tol, const double* resscale,
+                     int64_t maxiter, double* lhs, ipxgpu_cr_result* result,
+                     ipxgpu_interrupt_fn interrupt, void* user, double* resnorm_hist,
+                     int64_t hist_cap) {
+    return cr_host_entry(c, 0, true, rhs, tol, resscale, maxiter, lhs, result, interrupt, user,
+                         resnorm_hist, hist_cap);
+}
+
+int ipxgpu_pcr_solve_dev(ipxgpu_ctx* c, const void* rhs_dev, double tol, const void* resscale_dev,
+                         int64_t maxiter, void* lhs_dev, int zero_start,
+                         ipxgpu_cr_result* result) {
+    IPXGPU_TRY(check_ctx(c));
+    if (!rhs_dev || !lhs_dev) return fail(IPXGPU_ERR_ARGUMENT, "null vector");
+    if (!c->prepared) return fail(IPXGPU_ERR_STATE, "normal matrix not prepared");
+    if (!c->diag_ready) return fail(IPXGPU_ERR_STATE, "diagonal not factorized");
+    const auto t0 = std::chrono::steady_clock::now();
+    IPXGPU_TRY(ensure_cr_buffers(c, 0));
+    const size_t bytes = sizeof(double) * (size_t)c->m;
+    cudaStream_t s = c->stream;
+    IPXGPU_CUDA(cudaMemcpyAsync(c->v_rhs, rhs_dev, bytes, cudaMemcpyDeviceToDevice, s));
+    if (!zero_start)
+        IPXGPU_CUDA(cudaMemcpyAsync(c->v_y, lhs_dev, bytes, cudaMemcpyDeviceToDevice, s));
+    if (resscale_dev)
+        IPXGPU_CUDA(cudaMemcpyAsync(c->v_resscale, resscale_dev, bytes,
+                                    cudaMemcpyDeviceToDevice, s));
+    IPXGPU_TRY(run_cr(c, 0, true, zero_start != 0, resscale_dev != nullptr, tol, maxiter, result,
+                      nullptr, nullptr, 0));
+    IPXGPU_CUDA(cudaMemcpyAsync(lhs_dev, c->v_y, bytes, cudaMemcpyDeviceToDevice, s));
+    IPXGPU_CUDA(cudaStreamSynchronize(s));
+    if (result)
+        result->time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return IPXGPU_OK;
+}
+
+int ipxgpu_cr_solve(ipxgpu_ctx* c, int op, const double* rhs, double tol, const double* resscale,
+                    int64_t maxiter, double* lhs, ipxgpu_cr_result* result,
+                    ipxgpu_interrupt_fn interrupt, void* user, double* resnorm_hist,
+                    int64_t hist_cap) {
+    return cr_host_entry(c, op, false, rhs, tol, resscale, maxiter, lhs, result, interrupt, user,
+                         resnorm_hist, hist_cap);
+}
+
+// ---- KKTSolverDiag ----
+
+int ipxgpu_kktdiag_factorize(ipxgpu_ctx* c, const double* xl, const double* xu, const double* zl,
+                             const double* zu, double mu, double* W_out, double* resscale_out) {
+    IPXGPU_TRY(check_ctx(c));
+    if (c->nranks != 1)
+        return fail(IPXGPU_ERR_UNSUPPORTED, "kktdiag entry points need an unsharded context");
+    const long long nm = c->n + c->m;
+    if (!c->W_full) IPXGPU_TRY(dev_alloc(&c->W_full, (size_t)nm));
+    if (!c->resscale_kkt) IPXGPU_TRY(dev_alloc(&c->resscale_kkt, (size_t)c->m));
+    const int grid = grid_for(c, nm);
+    IPXGPU_TRY(ensure_reduce(c, grid));
+    c->kkt_factorized = false;
+    if (xl) {
+        if (!xu || !zl || !zu) return fail(IPXGPU_ERR_ARGUMENT, "incomplete iterate");
+        IPXGPU_TRY(ensure_nvecs(c));
+        // xl, xu, zl stream through the scratch vectors; zu through W_full's
+        // future tenant is not possible, so stage zu in the CR rhs-sized area
+        // only when it fits; otherwise reuse nvec[0] after consumption.
+        double* d_xl = c->nvec[0];
+        double* d_xu = c->nvec[1];
+        double* d_zl = c->nvec[2];
+        double* d_zu = nullptr;
+        IPXGPU_TRY(dev_alloc(&d_zu, (size_t)nm));
+        cudaStream_t s = c->stream;
+        auto up = [&](double* d, const double* h) {
+            return cudaMemcpyAsync(d, h, sizeof(double) * nm, cudaMemcpyHostToDevice, s);
+        };
+        cudaError_t e1 = up(d_xl, xl), e2 = up(d_xu, xu), e3 = up(d_zl, zl), e4 = up(d_zu, zu);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
+            cudaFree(d_zu);
+            return fail(IPXGPU_ERR_CUDA, "iterate upload failed");
+        }
+        kkt_weights_kernel<<<grid, kBlock, 0, s>>>(nm, d_xl, d_xu, d_zl, d_zu, c->W_full, c->red,
+                                                   c->scalars);
+        kkt_weights_fix_kernel<<<grid, kBlock, 0, s>>>(nm, c->n, c->W_full, c->resscale_kkt, mu,
+                                                       c->scalars);
+        c->launches += 2;
+        cudaError_t e5 = cudaStreamSynchronize(s);
+        cudaFree(d_zu);
+        if (e5 != cudaSuccess) return fail(IPXGPU_ERR_CUDA, cudaGetErrorString(e5));
+    } else {
+        fill_kernel<<<grid, kBlock, 0, c->stream>>>(nm, c->W_full, 1.0);
+        fill_kernel<<<grid_for(c, c->m), kBlock, 0, c->stream>>>(c->m, c->resscale_kkt, 1.0);
+        c->launches += 2;
+    }
+    IPXGPU_CUDA(cudaGetLastError());
+    IPXGPU_TRY(ipxgpu_normal_prepare_dev(c, c->W_full));
+    IPXGPU_TRY(launch_diag_build(c, c->Wc, c->Ws));
+    if (W_out)
+        IPXGPU_CUDA(cudaMemcpyAsync(W_out, c->W_full, sizeof(double) * nm, cudaMemcpyDeviceToHost,
+                                    c->stream));
+    if (resscale_out)
+        IPXGPU_CUDA(cudaMemcpyAsync(resscale_out, c->resscale_kkt, sizeof(double) * c->m,
+                                    cudaMemcpyDeviceToHost, c->stream));
+    IPXGPU_CUDA(cudaStreamSynchronize(c->stream));
+    c->kkt_factorized = true;
+    return IPXGPU_OK;
+}
+
+int ipxgpu_kktdiag_solve(ipxgpu_ctx* c, const double* a, const double* b, double tol,
+                         int64_t maxiter, double* x, double* y, ipxgpu_cr_result* result,
+                         ipxgpu_interrupt_fn interrupt, void* user) {
+    IPXGPU_TRY(check_ctx(c));
+    if (!c->kkt_factorized) return fail(IPXGPU_ERR_STATE, "kktdiag not factorized");
+    if (!a || !b || !x || !y) return fail(IPXGPU_ERR_ARGUMENT, "null vector");
+    const auto t0 = std::chrono::steady_clock::now();
+    const long long n = c->n, m = c->m, nm = n + m;
+    IPXGPU_TRY(ensure_nvecs(c));
+    IPXGPU_TRY(ensure_cr_buffers(c, 0));
+    cudaStream_t s = c->stream;
+    double* d_a = c->nvec[0];
+    double* d_u = c->nvec[1];  // W.*a, later x
+    double* d_b = c->xin;
+    IPXGPU_CUDA(cudaMemcpyAsync(d_a, a, sizeof(double) * nm, cudaMemcpyHostToDevice, s));
+    IPXGPU_CUDA(cudaMemcpyAsync(d_b, b, sizeof(double) * m, cudaMemcpyHostToDevice, s));
+    // rhs = -b + AI*(W.*a)  (reference src/kkt_solver_diag.cc:90-92)
+    mul_kernel<<<grid_for(c, n), kBlock, 0, s>>>(n, c->W_full, d_a, d_u);
+    mul_sub_kernel<<<grid_for(c, m), kBlock, 0, s>>>(m, c->W_full + n, d_a + n, d_b, c->ybuf);
+    c->launches += 2;
+    if (c->panels.empty())
+        IPXGPU_CUDA(cudaMemcpyAsync(c->v_rhs, c->ybuf, sizeof(double) * m,
+                                    cudaMemcpyDeviceToDevice, s));
+    for (size_t k = 0; k < c->panels.size(); k++) {
+        const Panel& P = c->panels[k];
+        OpRowAffine op{d_u, c->ybuf, c->v_rhs, 1.0, k == 0};
+        IPXGPU_TRY(launch_sweep(c, op, P.row_tiles, P.csr, nullptr));
+    }
+    // y = 0; PCR with resscale (reference :95-99)
+    IPXGPU_CUDA(cudaMemcpyAsync(c->v_resscale, c->resscale_kkt, sizeof(double) * m,
+                                cudaMemcpyDeviceToDevice, s));
+    IPXGPU_TRY(run_cr(c, 0, true, true, true, tol, maxiter, result, interrupt, user, 0));
+    // Recovery (reference :108-117): x[j] = W[j]*(a[j] - A[:,j]'y);
+    // x[n+i] = b[i] - sum_j x[j] a_ij.
+    for (size_t k = 0; k < c->panels.size(); k++) {
+        const Panel& P = c->panels[k];
+        OpColRecover op{c->v_y, c->W_full, d_a, d_u};
+        IPXGPU_TRY(launch_sweep(c, op, P.col_tiles, c->csc, nullptr));
+    }
+    if (c->panels.empty())
+        IPXGPU_CUDA(cudaMemcpyAsync(d_u + n, d_b, sizeof(double) * m, cudaMemcpyDeviceToDevice, s));
+    for (size_t k = 0; k < c->panels.size(); k++) {
+        const Panel& P = c->panels[k];
+        OpRowAffine op{d_u, d_b, d_u + n, -1.0, k == 0};
+        IPXGPU_TRY(launch_sweep(c, op, P.row_tiles, P.csr, nullptr));
+    }
+    IPXGPU_CUDA(cudaMemcpyAsync(x, d_u, sizeof(double) * nm, cudaMemcpyDeviceToHost, s));
+    IPXGPU_CUDA(cudaMemcpyAsync(y, c->v_y, sizeof(double) * m, cudaMemcpyDeviceToHost, s));
+    IPXGPU_CUDA(cudaStreamSynchronize(s));
+    if (result)
+        result->time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return IPXGPU_OK;
+}
+
+// ---- measurement helper ----
+
+int ipxgpu_time_normal_apply(ipxgpu_ctx* c, int reps, int flush_l2, double out_ms[3]) {
+    IPXGPU_TRY(check_ctx(c));
+    if (!c->prepared) return fail(IPXGPU_ERR_STATE, "normal matrix not prepared");
+    if (reps < 1 || !out_ms) return fail(IPXGPU_ERR_ARGUMENT, "invalid arguments");
+    if (c->nranks != 1) return fail(IPXGPU_ERR_UNSUPPORTED, "timing helper is single-shard");
+    if (flush_l2 && !c->flush_buf) {
+        c->flush_bytes = (size_t)256 << 20;
+        IPXGPU_TRY(dev_alloc(&c->flush_buf, c->flush_bytes));
+    }
+    cudaEvent_t e0, e1, e2;
+    IPXGPU_CUDA(cudaEventCreate(&e0));
+    IPXGPU_CUDA(cudaEventCreate(&e1));
+    IPXGPU_CUDA(cudaEventCreate(&e2));
+    double tot[3] = {0, 0, 0};
+    const int np = (int)c->panels.size();
+    int rc = IPXGPU_OK;
+    for (int r = 0; r < reps && rc == IPXGPU_OK; r++) {
+        if (flush_l2) cudaMemsetAsync(c->flush_buf, r & 0xff, c->flush_bytes, c->stream);
+        float t1 = 0.f, t2 = 0.f;
+        for (int k = 0; k < np && rc == IPXGPU_OK; k++) {
+            const Panel& P = c->panels[k];
+            cudaEventRecord(e0, c->stream);
+            OpColDotScale op1{c->xin, c->Wc, c->t};
+            rc = launch_sweep(c, op1, P.col_tiles, c->csc, nullptr);
+            cudaEventRecord(e1, c->stream);
+            OpRowGather op2{c->t, c->xin, c->Ws, c->ybuf, (int)c->m, k == 0, k == np - 1,
+                            kApplyPlain, kSlotNone};
+            if (rc == IPXGPU_OK) rc = launch_sweep(c, op2, P.row_tiles, P.csr, nullptr);
+            cudaEventRecord(e2, c->stream);
+            cudaEventSynchronize(e2);
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, e0, e1);
+            cudaEventElapsedTime(&b, e1, e2);
+            t1 += a;
+            t2 += b;
+        }
+        tot[1] += t1;
+        tot[2] += t2;
+        tot[0] += t1 + t2;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaEventDestroy(e2);
+    for (int k = 0; k < 3; k++) out_ms[k] = tot[k] / reps;
+    return rc;
+}
+
+}  // extern "C"
+
+#include "split_api.inc"
