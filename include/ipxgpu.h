@@ -77,6 +77,12 @@ int ipxgpu_get_layout(ipxgpu_ctx* ctx, int64_t out[8]);
 int ipxgpu_synchronize(ipxgpu_ctx* ctx);
 
 /* ---- multi-GPU: one context per rank, NCCL allreduce of the m-vector ---- */
+
+/* Contiguous column ranges balanced by nonzeros: rank r owns structural
+ * columns [bounds[r], bounds[r+1]). Pure host arithmetic (no device needed);
+ * ipxgpu_create uses the same rule when col_begin/col_end are -1. */
+int ipxgpu_partition_columns(int64_t n, const int64_t* AIp, int32_t nranks,
+                             int64_t* bounds);
 int ipxgpu_comm_unique_id(char id[128]);
 int ipxgpu_comm_init(ipxgpu_ctx* ctx, const char id[128]);
 

@@ -1,7 +1,7 @@
 """Build recipes for the native parts of ipx_b200 (in-tree, sm_100a only).
 
 * ``ipx_b200/_build/libipxgpu.so``   CUDA kernels + C ABI (include/ipxgpu.h); needs nvcc only.
-* ``ipx_b200/_build/libipx_gpu.so``  IPX with the six hot-path TUs replaced by the GPU
+* ``ipx_b200/_build/libipx_gpu.so``  IPX with the five hot-path TUs replaced by the GPU
   drop-ins of ipx_b200/host; needs the reference tree (compiled against its
   UNMODIFIED headers), so it is built where /root/reference exists and travels
   to the GPU box as a prebuilt file.
@@ -24,8 +24,10 @@ LIBIPXGPU = os.path.join(OUT, "libipxgpu.so")
 LIBIPX_GPU = os.path.join(OUT, "libipx_gpu.so")
 
 # Reference TUs replaced by ipx_b200/host/*_gpu.cc.
+# kkt_solver_basis.cc stays the reference's TU: its _Solve reaches the device through the
+# replaced ConjugateResiduals / SplittedNormalMatrix, its basis maintenance is host work.
 REPLACED = ["normal_matrix", "diagonal_precond", "conjugate_residuals", "splitted_normal_matrix",
-            "kkt_solver_diag", "kkt_solver_basis"]
+            "kkt_solver_diag"]
 ABSENT = ["basiclu_wrapper", "basiclu_kernel"]  # need the un-vendored BASICLU
 SHIMS = ["lu_provider", "sparse_lu", "lapack_min", "ipx_harness"]
 
@@ -111,6 +113,17 @@ def build_libipx_gpu(force=False):
     if force or _newer(LIBIPX_GPU, objs + [LIBIPXGPU]):
         _run([CXX, "-shared", "-Wl,-Bsymbolic", "-o", LIBIPX_GPU] + objs +
              [f"-L{OUT}", "-lipxgpu", "-Wl,-rpath,$ORIGIN"])
+    # Drop-in proof: the reference's own example and Catch suite, compiled from the
+    # reference tree unmodified, linked against the GPU build.
+    link = [f"-L{OUT}", "-lipx_gpu", "-lipxgpu", "-Wl,-rpath,$ORIGIN"]
+    afiro = os.path.join(OUT, "afiro_gpu")
+    if force or _newer(afiro, [LIBIPX_GPU]):
+        _run([CXX] + flags + [os.path.join(REF, "example", "afiro.cc"), "-o", afiro] + link)
+    check = os.path.join(OUT, "ipx_check_gpu")
+    if force or _newer(check, [LIBIPX_GPU]):
+        srcs = [os.path.join(REF, "check", f) for f in sorted(os.listdir(os.path.join(REF, "check")))
+                if f.endswith(".cc")]
+        _run([CXX] + flags + [f"-I{REF}/third_party"] + srcs + ["-o", check] + link)
     return LIBIPX_GPU
 
 

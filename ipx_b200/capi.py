@@ -35,7 +35,7 @@ class CrResult(C.Structure):
 INTERRUPT_FN = C.CFUNCTYPE(i64, C.c_void_p)
 
 EXPORTS = ("ipxgpu_default_options ipxgpu_last_error ipxgpu_device_count ipxgpu_create "
-           "ipxgpu_destroy ipxgpu_get_layout ipxgpu_synchronize ipxgpu_comm_unique_id "
+           "ipxgpu_destroy ipxgpu_get_layout ipxgpu_synchronize ipxgpu_partition_columns ipxgpu_comm_unique_id "
            "ipxgpu_comm_init ipxgpu_normal_prepare ipxgpu_normal_prepare_dev ipxgpu_normal_apply "
            "ipxgpu_normal_apply_dev ipxgpu_diag_factorize ipxgpu_diag_get ipxgpu_diag_set "
            "ipxgpu_diag_apply ipxgpu_pcr_solve ipxgpu_pcr_solve_dev ipxgpu_cr_solve ipxgpu_kktdiag_factorize "
@@ -90,6 +90,14 @@ def device_count():
     n = C.c_int(0)
     _check(load().ipxgpu_device_count(C.byref(n)))
     return n.value
+
+
+def partition_columns(n, AIp, nranks):
+    """Column shard bounds balanced by nonzeros (host arithmetic only)."""
+    AIp = _i64(AIp)
+    bounds = np.zeros(nranks + 1, np.int64)
+    _check(load().ipxgpu_partition_columns(i64(n), _i(AIp), C.c_int32(nranks), _i(bounds)))
+    return bounds
 
 
 def comm_unique_id():

@@ -405,6 +405,21 @@ int ipxgpu_device_count(int* count) {
     return IPXGPU_OK;
 }
 
+int ipxgpu_partition_columns(int64_t n, const int64_t* AIp, int32_t nranks, int64_t* bounds) {
+    if (n < 0 || !AIp || nranks < 1 || !bounds)
+        return fail(IPXGPU_ERR_ARGUMENT, "invalid partition arguments");
+    const int64_t nnzA = AIp[n] - AIp[0];
+    bounds[0] = 0;
+    for (int r = 1; r < nranks; r++) {
+        const int64_t target = AIp[0] + (int64_t)((__int128)nnzA * r / nranks);
+        int64_t cut = std::lower_bound(AIp, AIp + n + 1, target) - AIp;
+        if (cut > n) cut = n;
+        bounds[r] = std::max(cut, bounds[r - 1]);
+    }
+    bounds[nranks] = n;
+    return IPXGPU_OK;
+}
+
 void ipxgpu_destroy(ipxgpu_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
@@ -492,15 +507,10 @@ int ipxgpu_create(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp, co
     // Column shard: explicit, or balanced by nonzeros.
     int64_t cb = opt.col_begin, ce = opt.col_end;
     if (cb < 0 || ce < 0) {
-        const int64_t nnzA = AIp[n];
-        auto cut = [&](int r) -> int64_t {
-            if (r <= 0) return 0;
-            if (r >= opt.nranks) return n;
-            const int64_t target = nnzA / opt.nranks * r;
-            return std::lower_bound(AIp, AIp + n + 1, target) - AIp;
-        };
-        cb = cut(opt.rank);
-        ce = cut(opt.rank + 1);
+        std::vector<int64_t> bounds((size_t)opt.nranks + 1);
+        IPXGPU_TRY(ipxgpu_partition_columns(n, AIp, opt.nranks, bounds.data()));
+        cb = bounds[opt.rank];
+        ce = bounds[opt.rank + 1];
     }
     if (cb < 0 || ce < cb || ce > n) return fail(IPXGPU_ERR_ARGUMENT, "invalid column range");
     c->col_begin = cb;
@@ -536,7 +546,9 @@ int ipxgpu_create(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp, co
         const char* env_pc = std::getenv("IPXGPU_PANEL_COLS");
         if (opt.panel_cols <= 0 && env_pc) pc = std::max<int64_t>(1, std::atoll(env_pc));
         const int npanels = (int)std::max<int64_t>(1, (nloc + pc - 1) / pc);
-        c->panels.resize(nloc > 0 ? npanels : 0);
+        // A shard without structural columns still gets one (empty) panel: its
+        // row sweep carries the slack term and the fused dot product.
+        c->panels.resize(npanels);
         int max_grid = 1;
         for (int k = 0; k < (int)c->panels.size(); k++) {
             Panel& P = c->panels[k];

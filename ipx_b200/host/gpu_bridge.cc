@@ -1,0 +1,189 @@
+#include "gpu_bridge.h"
+
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+
+namespace ipxb200 {
+
+namespace {
+
+struct ModelEntry {
+    ipxgpu_ctx* ctx = nullptr;
+    unsigned long long generation = 0;
+    unsigned long long last_use = 0;
+    const double* values = nullptr;
+    ipx::Int entries = 0, rows = 0, cols = 0;
+    unsigned long long fingerprint = 0;
+    const double* hint_W = nullptr;
+    bool hint_weights = false, hint_diag = false;
+};
+
+struct Tables {
+    std::mutex mutex;
+    std::unordered_map<const ipx::Model*, ModelEntry> models;
+    std::unordered_map<const ipx::LinearOperator*, OperatorRecord> operators;
+    unsigned long long generation = 0, clock = 0;
+    ~Tables() {
+        for (auto& kv : models)
+            if (kv.second.ctx) ipxgpu_destroy(kv.second.ctx);
+    }
+};
+
+Tables& tables() {
+    static Tables t;
+    return t;
+}
+
+// Content fingerprint over a strided sample of AI (<= 64k entries): guards
+// against a new Model whose arrays were allocated at a recycled address.
+unsigned long long Fingerprint(const ipx::SparseMatrix& AI) {
+    unsigned long long h = 1469598103934665603ull;
+    auto mix = [&](unsigned long long v) {
+        h ^= v;
+        h *= 1099511628211ull;
+    };
+    const ipx::Int nz = AI.entries(), nc = AI.cols();
+    const ipx::Int step = nz > 65536 ? nz / 65536 : 1;
+    for (ipx::Int p = 0; p < nz; p += step) {
+        unsigned long long bits;
+        const double v = AI.value(p);
+        static_assert(sizeof bits == sizeof v, "double must be 64-bit");
+        std::memcpy(&bits, &v, sizeof bits);
+        mix(bits);
+        mix((unsigned long long)AI.index(p));
+    }
+    const ipx::Int cstep = nc > 65536 ? nc / 65536 : 1;
+    for (ipx::Int j = 0; j <= nc; j += cstep) mix((unsigned long long)AI.colptr()[j]);
+    return h;
+}
+
+ModelEntry* EntryOfContext(ipxgpu_ctx* ctx) {
+    for (auto& kv : tables().models)
+        if (kv.second.ctx == ctx) return &kv.second;
+    return nullptr;
+}
+
+size_t MaxContexts() {
+    const char* env = std::getenv("IPXGPU_MAX_CONTEXTS");
+    const long v = env ? std::atol(env) : 4;
+    return v < 1 ? 1 : (size_t)v;
+}
+
+}  // namespace
+
+void Check(int rc) {
+    if (rc == IPXGPU_OK) return;
+    if (rc == IPXGPU_ERR_OUT_OF_MEMORY) throw std::bad_alloc();
+    throw std::runtime_error(std::string("ipxgpu: ") + ipxgpu_last_error());
+}
+
+ContextRef ContextFor(const ipx::Model& model) {
+    Tables& t = tables();
+    std::lock_guard<std::mutex> lock(t.mutex);
+    const ipx::SparseMatrix& AI = model.AI();
+    const unsigned long long fp = Fingerprint(AI);
+    auto it = t.models.find(&model);
+    if (it != t.models.end()) {
+        ModelEntry& e = it->second;
+        if (e.ctx && e.values == AI.values() && e.entries == AI.entries() &&
+            e.rows == model.rows() && e.cols == model.cols() && e.fingerprint == fp) {
+            e.last_use = ++t.clock;
+            return ContextRef{e.ctx, e.generation};
+        }
+        if (e.ctx) ipxgpu_destroy(e.ctx);
+        t.models.erase(it);
+    }
+    // Model has no destructor hook: evict the least recently used context
+    // once the cache is full. Operators notice through the generation.
+    while (t.models.size() >= MaxContexts()) {
+        auto victim = t.models.begin();
+        for (auto jt = t.models.begin(); jt != t.models.end(); ++jt)
+            if (jt->second.last_use < victim->second.last_use) victim = jt;
+        if (victim->second.ctx) ipxgpu_destroy(victim->second.ctx);
+        t.models.erase(victim);
+    }
+    ipxgpu_options opt;
+    ipxgpu_default_options(&opt);
+    ipxgpu_ctx* ctx = nullptr;
+    Check(ipxgpu_create(&ctx, model.rows(), model.cols(), AI.colptr(), AI.rowidx(), AI.values(),
+                        &opt));
+    ModelEntry& e = t.models[&model];
+    e.ctx = ctx;
+    e.generation = ++t.generation;
+    e.last_use = ++t.clock;
+    e.values = AI.values();
+    e.entries = AI.entries();
+    e.rows = model.rows();
+    e.cols = model.cols();
+    e.fingerprint = fp;
+    return ContextRef{e.ctx, e.generation};
+}
+
+ContextRef CurrentContext(const ipx::Model& model) {
+    Tables& t = tables();
+    std::lock_guard<std::mutex> lock(t.mutex);
+    auto it = t.models.find(&model);
+    if (it == t.models.end() || !it->second.ctx) return ContextRef{};
+    it->second.last_use = ++t.clock;
+    return ContextRef{it->second.ctx, it->second.generation};
+}
+
+OperatorRecord& RecordOf(const ipx::LinearOperator* op) {
+    Tables& t = tables();
+    std::lock_guard<std::mutex> lock(t.mutex);
+    return t.operators[op];
+}
+
+OperatorRecord* FindRecord(const ipx::LinearOperator* op) {
+    Tables& t = tables();
+    std::lock_guard<std::mutex> lock(t.mutex);
+    auto it = t.operators.find(op);
+    return it == t.operators.end() ? nullptr : &it->second;
+}
+
+void Forget(const ipx::LinearOperator* op) {
+    Tables& t = tables();
+    std::lock_guard<std::mutex> lock(t.mutex);
+    t.operators.erase(op);
+}
+
+bool StillCurrent(const OperatorRecord& rec) {
+    if (!rec.model || !rec.ref.ctx) return false;
+    const ContextRef cur = CurrentContext(*rec.model);
+    return cur.ctx == rec.ref.ctx && cur.generation == rec.ref.generation;
+}
+
+void SetResidentHint(ipxgpu_ctx* ctx, const double* W) {
+    Tables& t = tables();
+    std::lock_guard<std::mutex> lock(t.mutex);
+    if (ModelEntry* e = EntryOfContext(ctx)) {
+        e->hint_W = W;
+        e->hint_weights = true;
+        e->hint_diag = true;
+    }
+}
+
+bool ConsumeWeightsHint(ipxgpu_ctx* ctx, const double* W) {
+    Tables& t = tables();
+    std::lock_guard<std::mutex> lock(t.mutex);
+    ModelEntry* e = EntryOfContext(ctx);
+    if (!e || !e->hint_weights || e->hint_W != W) return false;
+    e->hint_weights = false;
+    return true;
+}
+
+bool ConsumeDiagonalHint(ipxgpu_ctx* ctx, const double* W) {
+    Tables& t = tables();
+    std::lock_guard<std::mutex> lock(t.mutex);
+    ModelEntry* e = EntryOfContext(ctx);
+    if (!e || !e->hint_diag || e->hint_W != W) return false;
+    e->hint_diag = false;
+    return true;
+}
+
+}  // namespace ipxb200

@@ -246,6 +246,39 @@ def test_launch_counter_moves(problem):
     assert ctx.launch_count() > before
 
 
+def test_degenerate_shapes(capi, oracle):
+    """No structural columns (a dualized LP without constraints, reference
+    check/solver.cc:153-185) and no rows."""
+    # n = 0: AI = I
+    m = 3
+    AIp, AIi, AIx = np.arange(m + 1), np.arange(m), np.ones(m)
+    ctx = capi.Context(m, 0, AIp, AIi, AIx)
+    W = np.array([0.5, 2.0, 4.0])
+    x = np.array([1.0, -2.0, 3.0])
+    ctx.normal_prepare(W)
+    y, dot = ctx.normal_apply(x)
+    assert np.array_equal(y, W * x) and dot == float(x @ (W * x))
+    ctx.diag_factorize(W)
+    assert np.array_equal(ctx.diag_get(), W)
+    z, info = ctx.pcr_solve(x, 1e-12, None, -1)
+    assert info["errflag"] == 0 and np.allclose(z, x / W, rtol=1e-14)
+    Wk, rs = ctx.kktdiag_factorize(want_W=True)
+    xx, yy, info = ctx.kktdiag_solve(np.array([1.0, 2.0, 3.0]), np.array([0.5, 0.5, 0.5]), 1e-10, -1)
+    A = oracle.Csc(AIp, AIi, AIx)
+    x0, y0, info0 = oracle.kktdiag_solve(m, 0, A, Wk, np.ones(m), rs, np.array([1.0, 2.0, 3.0]),
+                                         np.array([0.5, 0.5, 0.5]), 1e-10, -1)
+    assert info["errflag"] == info0["errflag"] == 0
+    assert np.allclose(xx, x0, rtol=1e-12) and np.allclose(yy, y0, rtol=1e-12)
+    ctx.close()
+    # m = 0
+    n = 4
+    ctx = capi.Context(0, n, np.zeros(n + 1, np.int64), np.zeros(0, np.int64), np.zeros(0))
+    ctx.normal_prepare(np.ones(n))
+    y, dot = ctx.normal_apply(np.zeros(0))
+    assert y.size == 0
+    ctx.close()
+
+
 def test_interrupt_callback(capi):
     lp = lpgen.random_sparse_lp(2000, 20000, 8, 41)
     AIp, AIi, AIx = lp.solver_form()
