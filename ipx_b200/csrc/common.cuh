@@ -23,6 +23,8 @@ struct LongInfo {
     const int* first;      // [num_long+1] prefix over chunks
     double* partials;      // [total chunks]
     unsigned* counters;    // [num_long], zero between launches
+    double* dots;          // [num_long] fused-reduction share of each long segment
+    int num_long;
 };
 
 // Scratch for the "last CTA finishes the reduction" pattern.
@@ -123,7 +125,10 @@ __device__ __forceinline__ double block_max(double v, double* s_red) {
 __device__ __forceinline__ bool grid_reduce(const Reduce& red, double my_sum, double my_sum2,
                                             double my_max, double* s_red, int* s_flag,
                                             double* tot_sum, double* tot_sum2,
-                                            double* tot_max) {
+                                            double* tot_max, const double* extra = nullptr,
+                                            int nextra = 0) {
+    // `extra`: further addends of the first sum that were published (before
+    // the publisher's own ticket) at fixed slots, e.g. by long-segment CTAs.
     const int nblk = gridDim.x;
     if (threadIdx.x == 0) {
         red.partials[blockIdx.x] = my_sum;
@@ -142,6 +147,7 @@ __device__ __forceinline__ bool grid_reduce(const Reduce& red, double my_sum, do
         s2 += __ldcg(red.partials + nblk + b);
         mx = fmax(mx, __ldcg(red.partials + 2 * nblk + b));
     }
+    for (int b = threadIdx.x; b < nextra; b += kBlock) s += __ldcg(extra + b);
     s = block_sum(s, s_red);
     s2 = block_sum(s2, s_red);
     mx = block_max(mx, s_red);

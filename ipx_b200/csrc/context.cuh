@@ -46,7 +46,10 @@ struct TileSet {
     int* long_first = nullptr;
     double* long_partials = nullptr;
     unsigned* long_counters = nullptr;
-    LongInfo info() const { return LongInfo{long_first, long_partials, long_counters}; }
+    double* long_dots = nullptr;
+    LongInfo info() const {
+        return LongInfo{long_first, long_partials, long_counters, long_dots, num_long};
+    }
 };
 
 // Compressed structure on the device (CSC or CSR), int32 indices.

@@ -75,6 +75,8 @@ static int upload_tiles(TileSet* ts, const HostTiles& h, cudaStream_t s) {
     IPXGPU_TRY(upload(&ts->long_first, h.long_first, s));
     IPXGPU_TRY(dev_alloc(&ts->long_partials, (size_t)h.long_first.back()));
     IPXGPU_TRY(dev_alloc(&ts->long_counters, (size_t)ts->num_long));
+    IPXGPU_TRY(dev_alloc(&ts->long_dots, (size_t)ts->num_long));
+    IPXGPU_CUDA(cudaMemsetAsync(ts->long_dots, 0, sizeof(double) * std::max(1, ts->num_long), s));
     IPXGPU_CUDA(cudaMemsetAsync(ts->long_counters, 0,
                                 sizeof(unsigned) * std::max(1, ts->num_long), s));
     return IPXGPU_OK;
@@ -85,6 +87,7 @@ static void free_tiles(TileSet* ts) {
     dev_free(ts->long_first);
     dev_free(ts->long_partials);
     dev_free(ts->long_counters);
+    dev_free(ts->long_dots);
 }
 
 static void free_matrix(DevMatrix* A) {

@@ -58,7 +58,9 @@ seg_sweep_kernel(Op op, const Tile* __restrict__ tiles, const int* __restrict__ 
                     double tot = 0.0;
                     for (int c = 0; c < nch; c++) tot += __ldcg(li.partials + base + c);
                     li.counters[tile.long_id] = 0u;
-                    acc += op.epilogue(tile.seg0, tot);
+                    // Fixed slot, so the fused sum does not depend on which
+                    // chunk's CTA happened to finish last.
+                    li.dots[tile.long_id] = op.epilogue(tile.seg0, tot);
                 }
             }
         }
@@ -103,7 +105,8 @@ seg_sweep_kernel(Op op, const Tile* __restrict__ tiles, const int* __restrict__ 
     if (Op::kReduce) {
         const double mine = block_sum(acc, s_red);
         double tot_sum, tot_sum2, tot_max;
-        if (grid_reduce(red, mine, 0.0, 0.0, s_red, &s_flag, &tot_sum, &tot_sum2, &tot_max)) {
+        if (grid_reduce(red, mine, 0.0, 0.0, s_red, &s_flag, &tot_sum, &tot_sum2, &tot_max,
+                        li.dots, li.num_long)) {
             if (tid == 0) op.finalize(tot_sum, st);
         }
     }
