@@ -74,6 +74,9 @@ void ipxgpu_destroy(ipxgpu_ctx* ctx);
  * out = [m, n, nnz_local, col_begin, col_end, num_panels, csc_tiles,
  *        csr_tiles]. */
 int ipxgpu_get_layout(ipxgpu_ctx* ctx, int64_t out[8]);
+/* Tiling of the two sweeps of the normal-matrix apply, 8 values per sweep:
+ * [enabled, VB, SB, NVB, NSB, K, nparts, nitems] (sweep 1, then sweep 2). */
+int ipxgpu_get_tiling(ipxgpu_ctx* ctx, int64_t out[16]);
 int ipxgpu_synchronize(ipxgpu_ctx* ctx);
 
 /* ---- multi-GPU: one context per rank, NCCL allreduce of the m-vector ---- */

@@ -35,7 +35,7 @@ class CrResult(C.Structure):
 INTERRUPT_FN = C.CFUNCTYPE(i64, C.c_void_p)
 
 EXPORTS = ("ipxgpu_default_options ipxgpu_last_error ipxgpu_device_count ipxgpu_create "
-           "ipxgpu_destroy ipxgpu_get_layout ipxgpu_synchronize ipxgpu_partition_columns ipxgpu_comm_unique_id "
+           "ipxgpu_destroy ipxgpu_get_layout ipxgpu_get_tiling ipxgpu_synchronize ipxgpu_partition_columns ipxgpu_comm_unique_id "
            "ipxgpu_comm_init ipxgpu_normal_prepare ipxgpu_normal_prepare_dev ipxgpu_normal_apply "
            "ipxgpu_normal_apply_dev ipxgpu_diag_factorize ipxgpu_diag_get ipxgpu_diag_set "
            "ipxgpu_diag_apply ipxgpu_pcr_solve ipxgpu_pcr_solve_dev ipxgpu_cr_solve ipxgpu_kktdiag_factorize "
@@ -139,6 +139,12 @@ class Context:
         _check(self.lib.ipxgpu_get_layout(self.h, out))
         keys = "m n nnz_local col_begin col_end num_panels csc_tiles csr_tiles".split()
         return dict(zip(keys, list(out)))
+
+    def tiling(self):
+        out = (i64 * 16)()
+        _check(self.lib.ipxgpu_get_tiling(self.h, out))
+        keys = "enabled VB SB NVB NSB K nparts nitems".split()
+        return {"sweep1": dict(zip(keys, list(out)[:8])), "sweep2": dict(zip(keys, list(out)[8:]))}
 
     def synchronize(self):
         _check(self.lib.ipxgpu_synchronize(self.h))

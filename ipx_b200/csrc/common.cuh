@@ -98,7 +98,7 @@ __device__ __forceinline__ double block_sum(double v, double* s_red) {
     if (threadIdx.x == 0) {
         v = s_red[0];
 #pragma unroll
-        for (int w = 1; w < kWarps; w++) v += s_red[w];
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) v += s_red[w];
     }
     return v;
 }
@@ -113,7 +113,7 @@ __device__ __forceinline__ double block_max(double v, double* s_red) {
     if (threadIdx.x == 0) {
         v = s_red[0];
 #pragma unroll
-        for (int w = 1; w < kWarps; w++) v = fmax(v, s_red[w]);
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) v = fmax(v, s_red[w]);
     }
     return v;
 }
@@ -142,12 +142,12 @@ __device__ __forceinline__ bool grid_reduce(const Reduce& red, double my_sum, do
     if (!*s_flag) return false;
     __threadfence();
     double s = 0.0, s2 = 0.0, mx = 0.0;
-    for (int b = threadIdx.x; b < nblk; b += kBlock) {
+    for (int b = threadIdx.x; b < nblk; b += blockDim.x) {
         s += __ldcg(red.partials + b);
         s2 += __ldcg(red.partials + nblk + b);
         mx = fmax(mx, __ldcg(red.partials + 2 * nblk + b));
     }
-    for (int b = threadIdx.x; b < nextra; b += kBlock) s += __ldcg(extra + b);
+    for (int b = threadIdx.x; b < nextra; b += blockDim.x) s += __ldcg(extra + b);
     s = block_sum(s, s_red);
     s2 = block_sum(s2, s_red);
     mx = block_max(mx, s_red);

@@ -246,6 +246,40 @@ def test_launch_counter_moves(problem):
     assert ctx.launch_count() > before
 
 
+@pytest.mark.parametrize("kind", ["random_mid", "transport", "ragged"])
+def test_tiled_sweeps_opt_in(capi, oracle, kind, monkeypatch):
+    """The shared-memory tiled sweeps (IPXGPU_SWEEP=tiled) give the same operator."""
+    monkeypatch.setenv("IPXGPU_SWEEP", "tiled")
+    lp = _case(kind)
+    m, n = lp.m, lp.n
+    AIp, AIi, AIx = lp.solver_form()
+    ctx = capi.Context(m, n, AIp, AIi, AIx)
+    monkeypatch.delenv("IPXGPU_SWEEP")
+    A = oracle.Csc(AIp, AIi, AIx)
+    tiling = ctx.tiling()
+    if kind == "random_mid":
+        assert tiling["sweep1"]["enabled"] == 1 and tiling["sweep2"]["enabled"] == 1
+    x = np.random.default_rng(19).standard_normal(m)
+    for regime in ("mid", "wide", "null"):
+        W = None if regime == "null" else lpgen.weights(n + m, regime, 5)
+        ctx.normal_prepare(W)
+        y, dot = ctx.normal_apply(x)
+        y0, dot0 = oracle.normal_apply(m, n, A, W, x)
+        assert rel_err(y, y0) <= APPLY_TOL
+        assert abs(dot - dot0) <= APPLY_TOL * np.abs(x * y0).sum()
+        y2, dot2 = ctx.normal_apply(x)
+        assert np.array_equal(y, y2) and dot == dot2
+    W = lpgen.weights(n + m, "mid", 7)
+    ctx.normal_prepare(W)
+    ctx.diag_factorize(None, use_prepared=True)
+    rhs = np.random.default_rng(20).standard_normal(m)
+    z, info = ctx.pcr_solve(rhs, 1e-8, None, -1)
+    Cz, _ = oracle.normal_apply(m, n, A, W, z)
+    if info["errflag"] == 0:
+        assert np.abs(rhs - Cz).max() <= 1e-8 * (1 + 1e-6) + 1e-12
+    ctx.close()
+
+
 def test_degenerate_shapes(capi, oracle):
     """No structural columns (a dualized LP without constraints, reference
     check/solver.cc:153-185) and no rows."""

@@ -27,6 +27,7 @@ W = lpgen.weights(n + m, "mid", 1003)
 ctx.normal_prepare(W)
 ctx.diag_factorize(None, use_prepared=True)
 print(ctx.layout())
+print(ctx.tiling())
 print(ctx.time_normal_apply(args.reps, flush_l2=True))
 if args.pcr:
     rhs = np.random.default_rng(3).standard_normal(m)
