@@ -42,6 +42,7 @@ M_ROWS = 100_000
 N_COLS = 1_000_000
 NNZ_PER_COL = 10
 SEED = 1002
+NCU_TRAFFIC_BYTES_PER_APPLY = 271_440_000  # see roofline.traffic below
 
 
 def algorithmic_bytes(m, n, nnzA):
@@ -309,7 +310,13 @@ def run_gpu(args):
                     "h2d_bytes_per_step": 16 * m, "d2h_bytes_per_step": 8 * m},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak,
+                         # dram__bytes_read+write of sweep 1 + sweep 2 per apply, from the
+                         # ncu --set full capture profiles/r01_ncu_full_sweeps_c2.csv
+                         # (137.4 MB + 134.0 MB); only valid for the 1-GPU C2 workload.
+                         "traffic": NCU_TRAFFIC_BYTES_PER_APPLY if world == 1 else None,
+                         "traffic_source": "profiles/r01_ncu_full_sweeps_c2.csv",
+                         "peak_source": peak_src,
                          "kernel": "seg_sweep_kernel<OpColDotScale> + seg_sweep_kernel<OpRowGather>",
                          "algorithmic_bytes_per_apply": bytes_apply,
                          "apply_us_in_loop": 1e6 * t_apply,

@@ -1,0 +1,73 @@
+"""End-to-end LP solves through the unchanged ipx_c.h API with the reference CPU
+build and with the GPU drop-in build; prints the counters and phase times of
+ipx_info side by side (solver level)."""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ipx_b200 import ipxlib, lpgen  # noqa: E402
+
+KEYS = ("status status_ipm status_crossover iter kktiter1 kktiter2 objval time_total time_ipm1 "
+        "time_ipm2 time_starting_basis time_crossover time_kkt_factorize time_kkt_solve "
+        "time_maxvol time_cr1 time_cr1_AAt time_cr1_pre time_cr2 time_cr2_NNt time_cr2_B "
+        "time_cr2_Bt time_lu_invert updates_ipm mean_fill max_fill").split()
+
+
+def make(name):
+    kind, *dims = name.split(":")
+    d = [int(v) for v in dims]
+    if kind == "random":
+        return lpgen.random_sparse_lp(d[0], d[1], d[2], 1002)
+    if kind == "block":
+        return lpgen.block_angular_lp(d[0], d[1], d[2], 1003)
+    if kind == "transport":
+        return lpgen.transportation_lp(d[0], d[1], 1004)
+    if kind == "afiro":
+        return lpgen.afiro_lp()
+    raise ValueError(name)
+
+
+ap = argparse.ArgumentParser()
+ap.add_argument("lp", help="random:m:n:k | block:m:n:k | transport:S:T | afiro")
+ap.add_argument("--impl", default="both", choices=["both", "ref", "gpu"])
+ap.add_argument("--crossover", type=int, default=1)
+ap.add_argument("--switchiter", type=int, default=-1)
+ap.add_argument("--maxiter", type=int, default=300)
+ap.add_argument("--stop-at-switch", type=int, default=0,
+                help="-1: stop after the diagonal-preconditioned phase (reference debug parameter)")
+ap.add_argument("--out", default=None)
+args = ap.parse_args()
+
+lp = make(args.lp)
+print(f"LP {lp.name}: m={lp.m} n={lp.n} nnz={lp.nnz} optimum={lp.optimum}", flush=True)
+results = {}
+for impl, path in (("ref", ipxlib.REF_LIB), ("gpu", ipxlib.GPU_LIB)):
+    if args.impl not in ("both", impl):
+        continue
+    lib = ipxlib.IpxLibrary(path)
+    s = lib.lp_solver()
+    s.set_parameters(display=int(os.environ.get("IPX_DISPLAY", "0")), dualize=0,
+                     crossover=args.crossover, switchiter=args.switchiter,
+                     ipm_maxiter=args.maxiter, stop_at_switch=args.stop_at_switch)
+    assert s.load_model(lp) == 0
+    t0 = time.perf_counter()
+    s.solve()
+    wall = time.perf_counter() - t0
+    info = s.info()
+    results[impl] = {k: info[k] for k in KEYS}
+    results[impl]["wall"] = wall
+    s.close()
+    print(impl, json.dumps(results[impl]), flush=True)
+if len(results) == 2:
+    r, g = results["ref"], results["gpu"]
+    print("objective diff (rel):", abs(r["objval"] - g["objval"]) / max(1.0, abs(r["objval"])))
+    print("speed-up total:", r["time_total"] / g["time_total"],
+          " CR1:", r["time_cr1"] / max(g["time_cr1"], 1e-12),
+          " CR2:", r["time_cr2"] / max(g["time_cr2"], 1e-12) if g["time_cr2"] > 0 else None)
+if args.out:
+    with open(args.out, "w") as f:
+        json.dump({"lp": args.lp, "m": lp.m, "n": lp.n, "nnz": lp.nnz, "results": results}, f,
+                  indent=1)
