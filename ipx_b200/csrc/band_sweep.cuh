@@ -1,0 +1,523 @@
+// Banded gather-reduce sweep: out[s] = sum_{e in segment s} v[idx_e] * a_e with
+// the gathered vector staged in shared memory.
+//
+// Why: on B200 a divergent 8-byte global gather costs ~2 L1 wavefront cycles
+// per lane, which caps a sweep of A (normal_matrix.cc:67-75) near 20 % of HBM
+// bandwidth. A shared-memory gather costs ~0.2 cycles per lane. The gathered
+// vector does not fit in shared memory, so the matrix is re-tiled in two
+// dimensions at context creation:
+//
+//   bands  of the gather index space (VB entries, staged by TMA bulk copies
+//          into a ring of NBUF shared-memory buffers)
+//   blocks of the segment space      (SB accumulators in shared memory)
+//
+// An item = (segment block, run of consecutive bands) and is one CTA. Inside a
+// tile (block, band) every segment's entries form one run; runs are dealt to
+// the lanes of the CTA's consumer warps so that lane loads differ by at most
+// one entry, and a warp's share of the tile is stored as rows of 32 entries
+// (32 keys, 32 values: 384 contiguous bytes, fully coalesced). A warp's rows of
+// all the item's tiles are contiguous, so the warp streams them through a
+// register ring D rows deep without caring about tile boundaries; only the
+// consumption of the first row of a tile waits for the band's mbarrier.
+// A lane sums a run in a register and adds it to the segment's accumulator at
+// the run's last entry: no shuffles, no atomics, fixed summation order.
+//
+// One producer warp issues the bulk copies (cp.async.bulk, mbarrier
+// complete_tx); consumer warps release a buffer with an mbarrier arrive.
+#pragma once
+
+#include <stdint.h>
+
+#include <algorithm>
+#include <queue>
+#include <vector>
+
+#include "common.cuh"
+
+namespace ipxgpu {
+
+constexpr int kBandMaxVB = 32768;        // 15-bit band index
+constexpr unsigned kBandLast = 0x8000u;  // key flag: last entry of its run
+constexpr int kBandRowBytes = 384;       // 32 keys + 32 values
+constexpr int kBandMaxSteps = 256;       // bands per item (row table in shared memory)
+constexpr int kBandTailRows = 64;        // spare rows after the last one (>= 3*D)
+
+struct BandPlan {
+    int V = 0, S = 0;      // gather-vector length, number of segments
+    int VB = 0, SB = 0;    // band / block extents
+    int NVB = 0, NSB = 0;  // number of bands / blocks
+    int K = 0;             // bands per item
+    int nparts = 0;        // ceil(NVB / K): partial outputs per segment
+    int nitems = 0;        // NSB * nparts
+    int NW = 0;            // consumer warps per CTA
+    int NBUF = 2;          // band buffers
+    long long nnz = 0;
+    size_t smem = 0;
+};
+
+struct BandDev {
+    BandPlan plan;
+    int* row_ptr = nullptr;          // [nitems * NW * (K+1)]
+    unsigned char* stream = nullptr; // rows * 384 bytes
+    double* partials = nullptr;      // [nparts * S] when nparts > 1
+    long long rows = 0;
+    int debug = 0;
+};
+
+struct BandHost {
+    std::vector<int> row_ptr;
+    std::vector<uint32_t> stream;  // rows * 96 words
+    long long rows = 0;
+    long long pad_entries = 0;
+};
+
+enum BandMode : int {
+    kBandColScale = 0,  // out[s] = W ? acc*W[s] : acc
+    kBandRowFinal = 1,  // out[s] = (Ws ? x[s]*Ws[s] : 0) + acc, fused dot
+    kBandPartial = 2,   // partials[part*S + s] = acc
+};
+
+struct BandArgs {
+    const double* v;   // gather vector (16-byte aligned)
+    const double* W;   // kBandColScale: weights or nullptr
+    const double* Ws;  // kBandRowFinal: slack weights or nullptr
+    const double* x;   // kBandRowFinal: rhs for slack term and dot
+    double* out;       // t (col mode) or y (row mode, m+1 entries)
+    int apply_mode;    // ApplyMode for the fused scalar step
+    int slot;
+};
+
+// ---- PTX helpers (mbarrier + bulk copy) ----
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    const unsigned addr = smem_u32(bar);
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes,
+                                         uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ---- kernel ----
+//
+// Dynamic shared memory layout (bytes):
+//   [0, 64)                      full[NBUF], empty[NBUF] mbarriers (NBUF <= 4)
+//   [64, 64 + 4*NW*(K+1))        row table, padded to 16
+//   v[NBUF][VB] doubles
+//   acc[SB + 1] doubles          (slot SB receives the padding entries)
+// DBG (measurement only): bit 0 skips the staging, bit 1 the shared-memory work.
+template <int LD>
+__device__ __forceinline__ uint32_t band_ld_u32(const void* p) {
+    uint32_t v;
+    if (LD == 0) asm volatile("ld.global.cs.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    else if (LD == 1) asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    else if (LD == 2) asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    else asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+template <int LD>
+__device__ __forceinline__ double band_ld_f64(const void* p) {
+    double v;
+    if (LD == 0) asm volatile("ld.global.cs.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    else if (LD == 1) asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    else if (LD == 2) asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    else asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
+
+template <int NW, int D, int DBG = 0, int LD = 0>
+__global__ void __launch_bounds__((NW + 1) * 32, 1)
+band_sweep_kernel(BandDev T, BandArgs A, int mode, Reduce red, CrState* st) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double s_red[32];
+    __shared__ int s_flag;
+    if (st != nullptr && st->done) return;
+    const BandPlan& P = T.plan;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NBUF = P.NBUF;
+
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* empty = full + 4;
+    int* s_rows = reinterpret_cast<int*>(smem_raw + 64);
+    const size_t rows_bytes = (((size_t)NW * (P.K + 1) * 4) + 15) & ~(size_t)15;
+    double* v_buf = reinterpret_cast<double*>(smem_raw + 64 + rows_bytes);
+    double* acc_s = v_buf + (size_t)NBUF * P.VB;
+
+    const int sb = blockIdx.x / P.nparts;
+    const int part = blockIdx.x - sb * P.nparts;
+    const int seg_base = sb * P.SB;
+    const int nseg = min(P.SB, P.S - seg_base);
+    const int vb0 = part * P.K;
+    const int nk = min(P.NVB, vb0 + P.K) - vb0;
+    const int rot = sb % nk;
+
+    if (tid == 0) {
+        for (int b = 0; b < NBUF; b++) {
+            mbar_init(full + b, 1);
+            mbar_init(empty + b, NW);
+        }
+        mbar_fence_init();
+    }
+    for (int s = tid; s <= nseg; s += (NW + 1) * 32) acc_s[s] = 0.0;
+    {
+        const int* src = T.row_ptr + (size_t)blockIdx.x * NW * (P.K + 1);
+        for (int i = tid; i < NW * (P.K + 1); i += (NW + 1) * 32) s_rows[i] = src[i];
+    }
+    __syncthreads();
+
+    if (warp == NW) {
+        // ===== producer: stage the item's bands =====
+        if (lane == 0 && !(DBG & 1)) {
+            int b = 0;
+            unsigned par = 1;  // parity of the previous use of buffer b
+            for (int k = 0; k < nk; k++) {
+                if (k >= NBUF) mbar_wait(empty + b, par);
+                int r = k + rot;
+                if (r >= nk) r -= nk;
+                const int vbase = (vb0 + r) * P.VB;
+                const int vlen = min(P.VB, P.V - vbase);
+                double* dst = v_buf + (size_t)b * P.VB;
+                const unsigned bytes = (unsigned)(vlen & ~1) * 8u;
+                if (vlen & 1) dst[vlen - 1] = A.v[vbase + vlen - 1];
+                mbar_arrive_expect_tx(full + b, bytes);
+                // at most 16 KB per copy keeps several copies in flight
+                for (unsigned off = 0; off < bytes; off += 16384u) {
+                    const unsigned n = min(16384u, bytes - off);
+                    bulk_g2s(reinterpret_cast<unsigned char*>(dst) + off,
+                             reinterpret_cast<const unsigned char*>(A.v + vbase) + off, n,
+                             full + b);
+                }
+                if (++b == NBUF) {
+                    b = 0;
+                    par ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ===== consumers =====
+        // Rows [r_begin, r_end) of this warp, all tiles back to back. Two
+        // register batches of D rows alternate: one is consumed while the
+        // other is in flight. The stream ends with 2*D spare rows, so batch
+        // loads need no bounds checks.
+        const int* rp = s_rows + warp * (P.K + 1);
+        const int r_begin = rp[0], r_end = rp[nk];
+        const unsigned char* lane_base = T.stream + (size_t)lane * 4;
+        uint32_t ka[D], kb[D];
+        double aa[D], ab[D];
+        auto load_batch = [&](uint32_t* kk, double* av, int r0) {
+            const unsigned char* p = lane_base + (size_t)r0 * kBandRowBytes;
+#pragma unroll
+            for (int u = 0; u < D; u++) {
+                kk[u] = band_ld_u32<LD>(p + u * kBandRowBytes);
+                av[u] = band_ld_f64<LD>(p + u * kBandRowBytes + 128 + lane * 4);
+            }
+        };
+        int k = -1, buf = -1;
+        unsigned par = 1;
+        int boundary = r_begin;
+        const double* v_s = v_buf;
+        double sum = 0.0;
+        double last_v = 0.0;
+        auto advance = [&](int rr) {
+            do {
+                if (k >= 0) {
+                    // the buffer's last gathered value must have arrived before release
+                    asm volatile("" ::"d"(last_v) : "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(empty + buf);
+                }
+                k++;
+                if (++buf == NBUF) buf = 0;
+                if (buf == 0) par ^= 1u;
+                if (!(DBG & 1)) mbar_wait(full + buf, par);
+                v_s = v_buf + (size_t)buf * P.VB;
+                boundary = rp[k + 1];
+            } while (rr == boundary && k < nk - 1);
+        };
+        auto consume_batch = [&](const uint32_t* kk, const double* av, int r0) {
+#pragma unroll
+            for (int u = 0; u < D; u++) {
+                const int rr = r0 + u;
+                if (rr < r_end) {
+                    if (rr == boundary) advance(rr);
+                    const uint32_t key = kk[u];
+                    const double a = av[u];
+                    if (!(DBG & 2)) {
+                        last_v = v_s[key & 0x7fffu];
+                        sum = sum + __dmul_rn(last_v, a);
+                        if (key & kBandLast) {
+                            acc_s[key >> 16] += sum;
+                            sum = 0.0;
+                        }
+                    } else {
+                        sum += a + __uint_as_float(key);
+                    }
+                }
+            }
+        };
+        load_batch(ka, aa, r_begin);
+        for (int r = r_begin; r < r_end; r += 2 * D) {
+            load_batch(kb, ab, r + D);
+            consume_batch(ka, aa, r);
+            load_batch(ka, aa, r + 2 * D);
+            consume_batch(kb, ab, r + D);
+        }
+        // tiles after this warp's last row: release and (so that no bulk copy
+        // is in flight when the CTA exits) wait for the remaining bands
+        while (k < nk - 1) advance(-1);
+        if (DBG & 2) acc_s[lane] = sum;
+    }
+    __syncthreads();
+
+    double dot = 0.0;
+    for (int s = tid; s < nseg; s += (NW + 1) * 32) {
+        const int g = seg_base + s;
+        const double a = acc_s[s];
+        if (mode == kBandColScale) {
+            A.out[g] = A.W ? __dmul_rn(a, A.W[g]) : a;
+        } else if (mode == kBandRowFinal) {
+            const double xv = A.x[g];
+            const double yv = (A.Ws ? __dmul_rn(xv, A.Ws[g]) : 0.0) + a;
+            A.out[g] = yv;
+            dot += __dmul_rn(xv, yv);
+        } else {
+            T.partials[(size_t)part * P.S + g] = a;
+        }
+    }
+    if (mode == kBandRowFinal) {
+        const double mine = block_sum(dot, s_red);
+        double ts, ts2, tm;
+        if (grid_reduce(red, mine, 0.0, 0.0, s_red, &s_flag, &ts, &ts2, &tm) && tid == 0) {
+            A.out[P.S] = ts;
+            if (st) after_apply(st, A.apply_mode, ts, A.slot);
+        }
+    }
+}
+
+// out = epilogue(sum over parts, in order) for sweeps that ran in partial mode.
+__global__ void __launch_bounds__(kBlock)
+band_combine_kernel(BandDev T, BandArgs A, int mode, Reduce red, CrState* st) {
+    __shared__ double s_red[kWarps];
+    __shared__ int s_flag;
+    if (st != nullptr && st->done) return;
+    const int S = T.plan.S, nparts = T.plan.nparts;
+    double dot = 0.0;
+    for (int g = blockIdx.x * kBlock + threadIdx.x; g < S; g += gridDim.x * kBlock) {
+        double acc = 0.0;
+        for (int p = 0; p < nparts; p++) acc += __ldcg(T.partials + (size_t)p * S + g);
+        if (mode == kBandColScale) {
+            A.out[g] = A.W ? __dmul_rn(acc, A.W[g]) : acc;
+        } else {
+            const double xv = A.x[g];
+            const double yv = (A.Ws ? __dmul_rn(xv, A.Ws[g]) : 0.0) + acc;
+            A.out[g] = yv;
+            dot += __dmul_rn(xv, yv);
+        }
+    }
+    if (mode == kBandRowFinal) {
+        const double mine = block_sum(dot, s_red);
+        double ts, ts2, tm;
+        if (grid_reduce(red, mine, 0.0, 0.0, s_red, &s_flag, &ts, &ts2, &tm) &&
+            threadIdx.x == 0) {
+            A.out[S] = ts;
+            if (st) after_apply(st, A.apply_mode, ts, A.slot);
+        }
+    }
+}
+
+// ---- host side ----
+
+inline size_t band_smem_bytes(const BandPlan& P) {
+    const size_t rows_bytes = (((size_t)P.NW * (P.K + 1) * 4) + 15) & ~(size_t)15;
+    return 64 + rows_bytes + (size_t)P.NBUF * P.VB * 8 + ((size_t)P.SB + 1) * 8;
+}
+
+// Fills the derived fields of a plan from (V, S, VB, SB, K, NW, NBUF).
+inline bool band_finish_plan(BandPlan* P) {
+    if (P->V <= 0 || P->S <= 0 || P->VB <= 0 || P->SB <= 0) return false;
+    if (P->VB > kBandMaxVB || (P->VB & 1) || P->SB > 65535) return false;
+    P->NVB = (P->V + P->VB - 1) / P->VB;
+    P->NSB = (P->S + P->SB - 1) / P->SB;
+    if (P->K <= 0 || P->K > P->NVB) P->K = P->NVB;
+    if (P->K > kBandMaxSteps) return false;
+    P->nparts = (P->NVB + P->K - 1) / P->K;
+    P->nitems = P->NSB * P->nparts;
+    P->smem = band_smem_bytes(*P);
+    return P->smem <= 227 * 1024;
+}
+
+// Re-tiles a compressed structure (segments ptr[0..S], gather indices idx in
+// [0,V), ascending per segment) into the banded row streams. Returns false when
+// a run is longer than max_run (such structures suit the generic sweep).
+inline bool band_build(const BandPlan& P, const int* ptr, const int* idx, const double* val,
+                       BandHost* H, int max_run = 64) {
+    const int S = P.S, VB = P.VB, SB = P.SB, NVB = P.NVB, NSB = P.NSB, NW = P.NW;
+    const size_t ntiles = (size_t)NSB * NVB;
+    struct Run {
+        int first;            // first entry in idx/val
+        unsigned short seg;   // local segment
+        unsigned short len;
+    };
+    // pass 1: runs per (tile, warp). A segment belongs to the same warp in
+    // every tile of its block (local segment % NW), so all additions to one
+    // accumulator are issued by one warp, in program order; warps never have
+    // to synchronise with each other between tiles.
+    const size_t ntw = ntiles * (size_t)NW;
+    std::vector<long long> tcount(ntw + 1, 0);
+    for (int s = 0; s < S; s++) {
+        const size_t trow = (size_t)(s / SB) * NVB;
+        const int w = (s % SB) % NW;
+        int p = ptr[s];
+        const int pe = ptr[s + 1];
+        while (p < pe) {
+            const int vb = idx[p] / VB;
+            int q = p + 1;
+            while (q < pe && idx[q] / VB == vb) q++;
+            if (q - p > max_run) return false;
+            tcount[(trow + vb) * NW + w + 1]++;
+            p = q;
+        }
+    }
+    for (size_t t = 0; t < ntw; t++) tcount[t + 1] += tcount[t];
+    std::vector<Run> runs((size_t)tcount[ntw]);
+    {
+        std::vector<long long> next(tcount.begin(), tcount.end() - 1);
+        for (int s = 0; s < S; s++) {
+            const size_t trow = (size_t)(s / SB) * NVB;
+            const int w = (s % SB) % NW;
+            int p = ptr[s];
+            const int pe = ptr[s + 1];
+            while (p < pe) {
+                const int vb = idx[p] / VB;
+                int q = p + 1;
+                while (q < pe && idx[q] / VB == vb) q++;
+                runs[(size_t)next[(trow + vb) * NW + w]++] =
+                    Run{p, (unsigned short)(s % SB), (unsigned short)(q - p)};
+                p = q;
+            }
+        }
+    }
+    // pass 2: deal the runs of every (tile, warp) to the 32 lanes, longest
+    // first, each to the least loaded lane (ties: lowest lane), so loads differ
+    // by <= 1 whenever there are enough short runs. place[r] = lane << 16 | offset.
+    std::vector<uint32_t> place(runs.size());
+    std::vector<int> trows(ntw, 0);  // rows of (tile, warp)
+    {
+        std::vector<long long> order;
+        std::vector<int> bucket_start;
+        for (size_t t = 0; t < ntw; t++) {
+            const long long r0 = tcount[t], r1 = tcount[t + 1];
+            const int nr = (int)(r1 - r0);
+            if (nr == 0) continue;
+            int maxlen = 0;
+            for (long long r = r0; r < r1; r++) maxlen = std::max(maxlen, (int)runs[r].len);
+            bucket_start.assign(maxlen + 2, 0);
+            for (long long r = r0; r < r1; r++) bucket_start[maxlen - runs[r].len + 1]++;
+            for (int b = 0; b <= maxlen; b++) bucket_start[b + 1] += bucket_start[b];
+            order.resize(nr);
+            for (long long r = r0; r < r1; r++)
+                order[bucket_start[maxlen - runs[r].len]++] = r;
+            int load[32];
+            for (int l = 0; l < 32; l++) load[l] = 0;
+            for (int k = 0; k < nr; k++) {
+                const long long r = order[k];
+                int best = 0;
+                for (int l = 1; l < 32; l++)
+                    if (load[l] < load[best]) best = l;
+                place[r] = ((uint32_t)best << 16) | (uint32_t)load[best];
+                load[best] += runs[r].len;
+            }
+            int mx = 0;
+            for (int l = 0; l < 32; l++) mx = std::max(mx, load[l]);
+            trows[t] = mx;
+        }
+    }
+    // pass 3: row offsets in stream order (item, warp, step)
+    const int K = P.K, nparts = P.nparts;
+    H->row_ptr.assign((size_t)P.nitems * NW * (K + 1), 0);
+    std::vector<long long> tile_warp_row(ntiles * (size_t)NW, 0);
+    long long rows = 0;
+    for (int sb = 0; sb < NSB; sb++) {
+        for (int part = 0; part < nparts; part++) {
+            const int item = sb * nparts + part;
+            const int vb0 = part * K;
+            const int nk = std::min(NVB, vb0 + K) - vb0;
+            const int rot = sb % nk;
+            for (int w = 0; w < NW; w++) {
+                int* rp = H->row_ptr.data() + ((size_t)item * NW + w) * (K + 1);
+                for (int k = 0; k < nk; k++) {
+                    int r = k + rot;
+                    if (r >= nk) r -= nk;
+                    const size_t t = (size_t)sb * NVB + vb0 + r;
+                    rp[k] = (int)rows;
+                    tile_warp_row[t * NW + w] = rows;
+                    rows += trows[t * NW + w];
+                }
+                for (int k = nk; k <= K; k++) rp[k] = (int)rows;
+                if (rows >= (long long)INT32_MAX / 2) return false;
+            }
+        }
+    }
+    H->rows = rows;
+    const long long rows_alloc = rows + kBandTailRows;  // spare rows: unchecked batch loads
+    // pass 4: fill; padding = (segment SB, last, index 0, value 0)
+    H->stream.assign((size_t)rows_alloc * 96, 0u);
+    {
+        const uint32_t padkey = ((uint32_t)SB << 16) | kBandLast;
+        for (long long r = 0; r < rows; r++) {
+            uint32_t* row = H->stream.data() + (size_t)r * 96;
+            for (int l = 0; l < 32; l++) row[l] = padkey;
+        }
+    }
+    long long filled = 0;
+    for (size_t t = 0; t < ntw; t++) {
+        const int vb = (int)((t / NW) % NVB);
+        for (long long r = tcount[t]; r < tcount[t + 1]; r++) {
+            const Run& R = runs[r];
+            const int l = (int)(place[r] >> 16), off = (int)(place[r] & 0xffffu);
+            const long long row0 = tile_warp_row[t] + off;
+            for (int j = 0; j < R.len; j++) {
+                uint32_t* row = H->stream.data() + (size_t)(row0 + j) * 96;
+                uint32_t key = ((uint32_t)R.seg << 16) | (uint32_t)(idx[R.first + j] - vb * VB);
+                if (j == R.len - 1) key |= kBandLast;
+                row[l] = key;
+                reinterpret_cast<double*>(row + 32)[l] = val[R.first + j];
+            }
+            filled += R.len;
+        }
+    }
+    H->pad_entries = rows * 32 - filled;
+    return true;
+}
+
+}  // namespace ipxgpu

@@ -96,7 +96,7 @@ inline int upload(T** dst, const std::vector<T>& src, cudaStream_t s) {
 }
 
 struct SplitOperator;  // split.cuh
-struct TiledSweep;     // tiled_sweep.cuh
+struct BandDev;        // band_sweep.cuh
 
 }  // namespace ipxgpu
 
@@ -149,9 +149,9 @@ struct ipxgpu_ctx {
     // basis path
     ipxgpu::SplitOperator* split = nullptr;
 
-    // shared-memory tiled sweeps of the normal-matrix apply (may be null)
-    ipxgpu::TiledSweep* tiled1 = nullptr;  // t = W .* (A'x): gather x, segments = columns
-    ipxgpu::TiledSweep* tiled2 = nullptr;  // y = A t: gather t, segments = rows
+    // banded shared-memory sweeps of the normal-matrix apply (may be null)
+    ipxgpu::BandDev* band1 = nullptr;  // t = W .* (A'x): gather x, segments = columns
+    ipxgpu::BandDev* band2 = nullptr;  // y = A t: gather t, segments = rows
 
     // L2 flush buffer for measurement helpers
     char* flush_buf = nullptr;

@@ -13,7 +13,7 @@
 #include "cr_kernels.cuh"
 #include "spmv_kernels.cuh"
 #include "split.cuh"
-#include "tiled_sweep.cuh"
+#include "band_plan.cuh"
 
 namespace ipxgpu {
 
@@ -172,18 +172,18 @@ static int launch_normal_apply_w(ipxgpu_ctx* c, const double* Wc, const double* 
     const int np = (int)c->panels.size();
     const bool sharded = c->nranks > 1;
     if (np == 0 || c->m == 0) return IPXGPU_OK;
-    const bool tiled1 = c->tiled1 != nullptr, tiled2 = c->tiled2 != nullptr;
-    if (tiled1) {
-        TiledArgs a1{x, Wc, nullptr, nullptr, c->t, kApplyPlain, kSlotNone};
-        IPXGPU_TRY(launch_tiled(c, *c->tiled1, a1, kTiledColScale, st));
+    const bool band1 = band_usable(c->band1, x), band2 = band_usable(c->band2, c->t);
+    if (band1) {
+        BandArgs a1{x, Wc, nullptr, nullptr, c->t, kApplyPlain, kSlotNone};
+        IPXGPU_TRY(launch_band(c, *c->band1, a1, kBandColScale, st));
     }
     for (int k = 0; k < np; k++) {
         const Panel& P = c->panels[k];
-        if (!tiled1) {
+        if (!band1) {
             OpColDotScale op1{x, Wc, c->t};
             IPXGPU_TRY(launch_sweep(c, op1, P.col_tiles, c->csc, st));
         }
-        if (tiled2) continue;
+        if (band2) continue;
         OpRowGather op2;
         op2.t = c->t;
         op2.x = x;
@@ -196,10 +196,10 @@ static int launch_normal_apply_w(ipxgpu_ctx* c, const double* Wc, const double* 
         op2.slot = slot;
         IPXGPU_TRY(launch_sweep(c, op2, P.row_tiles, P.csr, sharded ? nullptr : st));
     }
-    if (tiled2) {
-        TiledArgs a2{c->t, nullptr, (c->rank == 0) ? Ws : nullptr, x, y,
-                     sharded ? (int)kApplyPlain : mode, slot};
-        IPXGPU_TRY(launch_tiled(c, *c->tiled2, a2, kTiledRowFinal, sharded ? nullptr : st));
+    if (band2) {
+        BandArgs a2{c->t, nullptr, (c->rank == 0) ? Ws : nullptr, x, y,
+                    sharded ? (int)kApplyPlain : mode, slot};
+        IPXGPU_TRY(launch_band(c, *c->band2, a2, kBandRowFinal, sharded ? nullptr : st));
     }
     if (sharded) {
         IPXGPU_TRY(allreduce_sum(c, y, (size_t)c->m + 1));
@@ -442,8 +442,8 @@ void ipxgpu_destroy(ipxgpu_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     destroy_split(c);
-    if (c->tiled1) { free_tiled(c->tiled1); delete c->tiled1; }
-    if (c->tiled2) { free_tiled(c->tiled2); delete c->tiled2; }
+    if (c->band1) { free_band(c->band1); delete c->band1; }
+    if (c->band2) { free_band(c->band2); delete c->band2; }
     free_matrix(&c->csc);
     for (Panel& P : c->panels) {
         free_tiles(&P.col_tiles);
@@ -602,31 +602,32 @@ int ipxgpu_create(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp, co
             max_grid = std::max(max_grid, std::max(P.col_tiles.ntiles, P.row_tiles.ntiles));
             IPXGPU_CUDA(cudaStreamSynchronize(s));  // host vectors die here
         }
-        // Shared-memory tiled sweeps (tiled_sweep.cuh) are opt-in:
-        // IPXGPU_SWEEP=tiled uses them where the structure allows,
-        // IPXGPU_SWEEP=tiled-auto only where the re-reads of the gathered
-        // vector stay below 1.5x the matrix stream. Round-1 measurements put
-        // them level with the generic sweeps on the benchmark shape (DESIGN.md
-        // section 4), so the default is the generic path.
+        // Banded shared-memory sweeps (band_sweep.cuh) carry the normal-matrix
+        // apply wherever the structure suits them. IPXGPU_SWEEP=generic turns
+        // them off, IPXGPU_SWEEP=band forces them whenever a plan fits.
         {
             const char* env = std::getenv("IPXGPU_SWEEP");
-            const std::string how = env ? env : "generic";
-            const double ratio = how == "tiled" ? 1e30 : 1.5;
-            if ((how == "tiled" || how == "tiled-auto") && nnz > 0 && m > 0) {
-                TiledSweep plan;
-                if (plan_tiled(&plan, (int)m, (int)nloc, nnz, c->num_sms, ratio)) {
-                    c->tiled1 = new TiledSweep(plan);
-                    const int rc1 = build_tiled(c, c->tiled1, cp.data(), ci.data(), AIx + base);
+            const std::string how = env ? env : "auto";
+            const bool force = how == "band" || how == "tiled";
+            const double ratio = force ? 1e30 : 1.5;
+            const double max_pad = force ? 1.0 : 0.25;
+            if (how != "generic" && nnz > 0 && m > 0) {
+                BandPlan plan;
+                if (plan_band(&plan, (int)m, (int)nloc, nnz, c->num_sms, ratio)) {
+                    c->band1 = new BandDev();
+                    c->band1->plan = plan;
+                    const int rc1 = build_band(c, c->band1, cp.data(), ci.data(), AIx + base,
+                                               max_pad);
                     if (rc1 == IPXGPU_ERR_UNSUPPORTED) {  // structure suits the generic sweep
-                        free_tiled(c->tiled1);
-                        delete c->tiled1;
-                        c->tiled1 = nullptr;
+                        free_band(c->band1);
+                        delete c->band1;
+                        c->band1 = nullptr;
                     } else {
                         IPXGPU_TRY(rc1);
-                        max_grid = std::max(max_grid, c->tiled1->nitems);
+                        max_grid = std::max(max_grid, plan.nitems);
                     }
                 }
-                if (plan_tiled(&plan, (int)nloc, (int)m, nnz, c->num_sms, ratio)) {
+                if (plan_band(&plan, (int)nloc, (int)m, nnz, c->num_sms, ratio)) {
                     // full-shard CSR (rows ascending, columns ascending within a row)
                     std::vector<int> rp((size_t)m + 1, 0), rj((size_t)nnz);
                     std::vector<double> rx((size_t)nnz);
@@ -639,15 +640,17 @@ int ipxgpu_create(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp, co
                             rj[put] = j;
                             rx[put] = AIx[base + p];
                         }
-                    c->tiled2 = new TiledSweep(plan);
-                    const int rc2 = build_tiled(c, c->tiled2, rp.data(), rj.data(), rx.data());
+                    c->band2 = new BandDev();
+                    c->band2->plan = plan;
+                    const int rc2 = build_band(c, c->band2, rp.data(), rj.data(), rx.data(),
+                                               max_pad);
                     if (rc2 == IPXGPU_ERR_UNSUPPORTED) {
-                        free_tiled(c->tiled2);
-                        delete c->tiled2;
-                        c->tiled2 = nullptr;
+                        free_band(c->band2);
+                        delete c->band2;
+                        c->band2 = nullptr;
                     } else {
                         IPXGPU_TRY(rc2);
-                        max_grid = std::max(max_grid, c->tiled2->nitems);
+                        max_grid = std::max(max_grid, plan.nitems);
                     }
                 }
             }
@@ -687,13 +690,14 @@ int ipxgpu_get_layout(ipxgpu_ctx* c, int64_t out[8]) {
 
 int ipxgpu_get_tiling(ipxgpu_ctx* c, int64_t out[16]) {
     if (!c || !out) return fail(IPXGPU_ERR_ARGUMENT, "null argument");
-    const TiledSweep* ts[2] = {c->tiled1, c->tiled2};
+    const BandDev* ts[2] = {c->band1, c->band2};
     for (int k = 0; k < 2; k++) {
         int64_t* o = out + 8 * k;
         for (int j = 0; j < 8; j++) o[j] = 0;
         if (!ts[k]) continue;
-        o[0] = 1; o[1] = ts[k]->VB; o[2] = ts[k]->SB; o[3] = ts[k]->NVB; o[4] = ts[k]->NSB;
-        o[5] = ts[k]->K; o[6] = ts[k]->nparts; o[7] = ts[k]->nitems;
+        const BandPlan& P = ts[k]->plan;
+        o[0] = 1; o[1] = P.VB; o[2] = P.SB; o[3] = P.NVB; o[4] = P.NSB;
+        o[5] = P.K; o[6] = P.nparts; o[7] = P.nitems;
     }
     return IPXGPU_OK;
 }
@@ -1084,12 +1088,12 @@ int ipxgpu_time_normal_apply(ipxgpu_ctx* c, int reps, int flush_l2, double out_m
     for (int r = 0; r < reps && rc == IPXGPU_OK; r++) {
         if (flush_l2) cudaMemsetAsync(c->flush_buf, r & 0xff, c->flush_bytes, c->stream);
         float t1 = 0.f, t2 = 0.f;
-        if (c->tiled1 || c->tiled2) {
-            // A tiled sweep is a whole-matrix stage: time the two stages.
+        if (c->band1 || c->band2) {
+            // A banded sweep is a whole-matrix stage: time the two stages.
             cudaEventRecord(e0, c->stream);
-            if (c->tiled1) {
-                TiledArgs a1{c->xin, c->Wc, nullptr, nullptr, c->t, kApplyPlain, kSlotNone};
-                rc = launch_tiled(c, *c->tiled1, a1, kTiledColScale, nullptr);
+            if (c->band1) {
+                BandArgs a1{c->xin, c->Wc, nullptr, nullptr, c->t, kApplyPlain, kSlotNone};
+                rc = launch_band(c, *c->band1, a1, kBandColScale, nullptr);
             } else {
                 for (int k = 0; k < np && rc == IPXGPU_OK; k++) {
                     OpColDotScale op1{c->xin, c->Wc, c->t};
@@ -1097,9 +1101,9 @@ int ipxgpu_time_normal_apply(ipxgpu_ctx* c, int reps, int flush_l2, double out_m
                 }
             }
             cudaEventRecord(e1, c->stream);
-            if (rc == IPXGPU_OK && c->tiled2) {
-                TiledArgs a2{c->t, nullptr, c->Ws, c->xin, c->ybuf, kApplyPlain, kSlotNone};
-                rc = launch_tiled(c, *c->tiled2, a2, kTiledRowFinal, nullptr);
+            if (rc == IPXGPU_OK && c->band2) {
+                BandArgs a2{c->t, nullptr, c->Ws, c->xin, c->ybuf, kApplyPlain, kSlotNone};
+                rc = launch_band(c, *c->band2, a2, kBandRowFinal, nullptr);
             } else {
                 for (int k = 0; k < np && rc == IPXGPU_OK; k++) {
                     OpRowGather op2{c->t, c->xin, c->Ws, c->ybuf, (int)c->m, k == 0, k == np - 1,
@@ -1112,7 +1116,7 @@ int ipxgpu_time_normal_apply(ipxgpu_ctx* c, int reps, int flush_l2, double out_m
             cudaEventElapsedTime(&t1, e0, e1);
             cudaEventElapsedTime(&t2, e1, e2);
         }
-        for (int k = 0; k < np && rc == IPXGPU_OK && !(c->tiled1 || c->tiled2); k++) {
+        for (int k = 0; k < np && rc == IPXGPU_OK && !(c->band1 || c->band2); k++) {
             const Panel& P = c->panels[k];
             cudaEventRecord(e0, c->stream);
             OpColDotScale op1{c->xin, c->Wc, c->t};

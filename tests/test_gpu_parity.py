@@ -247,9 +247,10 @@ def test_launch_counter_moves(problem):
 
 
 @pytest.mark.parametrize("kind", ["random_mid", "transport", "ragged"])
-def test_tiled_sweeps_opt_in(capi, oracle, kind, monkeypatch):
-    """The shared-memory tiled sweeps (IPXGPU_SWEEP=tiled) give the same operator."""
-    monkeypatch.setenv("IPXGPU_SWEEP", "tiled")
+def test_band_sweeps_forced(capi, oracle, kind, monkeypatch):
+    """The banded shared-memory sweeps, forced on small shapes (IPXGPU_SWEEP=band), give the
+    same operator as the oracle."""
+    monkeypatch.setenv("IPXGPU_SWEEP", "band")
     lp = _case(kind)
     m, n = lp.m, lp.n
     AIp, AIi, AIx = lp.solver_form()
@@ -278,6 +279,49 @@ def test_tiled_sweeps_opt_in(capi, oracle, kind, monkeypatch):
     if info["errflag"] == 0:
         assert np.abs(rhs - Cz).max() <= 1e-8 * (1 + 1e-6) + 1e-12
     ctx.close()
+
+
+def test_band_sweeps_auto(capi, oracle):
+    """A shape large enough that the planner picks the banded sweeps on its own:
+    apply parity in every weight regime, run-to-run determinism, the generic
+    sweeps (IPXGPU_SWEEP=generic) as a second opinion, and a PCR solve."""
+    import os
+    lp = lpgen.random_sparse_lp(20000, 400000, 10, 31)
+    m, n = lp.m, lp.n
+    AIp, AIi, AIx = lp.solver_form()
+    ctx = capi.Context(m, n, AIp, AIi, AIx)
+    tiling = ctx.tiling()
+    assert tiling["sweep1"]["enabled"] == 1 and tiling["sweep2"]["enabled"] == 1, tiling
+    os.environ["IPXGPU_SWEEP"] = "generic"
+    try:
+        ctx_gen = capi.Context(m, n, AIp, AIi, AIx)
+    finally:
+        del os.environ["IPXGPU_SWEEP"]
+    assert ctx_gen.tiling()["sweep1"]["enabled"] == 0
+    A = oracle.Csc(AIp, AIi, AIx)
+    x = np.random.default_rng(41).standard_normal(m)
+    for regime in ("ones", "mid", "wide", "null"):
+        W = None if regime == "null" else lpgen.weights(n + m, regime, 6)
+        ctx.normal_prepare(W)
+        ctx_gen.normal_prepare(W)
+        y, dot = ctx.normal_apply(x)
+        y0, dot0 = oracle.normal_apply(m, n, A, W, x)
+        assert rel_err(y, y0) <= APPLY_TOL
+        assert abs(dot - dot0) <= APPLY_TOL * np.abs(x * y0).sum()
+        y2, dot2 = ctx.normal_apply(x)
+        assert np.array_equal(y, y2) and dot == dot2
+        yg, dotg = ctx_gen.normal_apply(x)
+        assert rel_err(yg, y0) <= APPLY_TOL
+    W = lpgen.weights(n + m, "mid", 8)
+    ctx.normal_prepare(W)
+    ctx.diag_factorize(None, use_prepared=True)
+    rhs = np.random.default_rng(42).standard_normal(m)
+    z, info = ctx.pcr_solve(rhs, 1e-8, None, -1)
+    Cz, _ = oracle.normal_apply(m, n, A, W, z)
+    assert info["errflag"] == 0
+    assert np.abs(rhs - Cz).max() <= 1e-8 * (1 + 1e-6) + 1e-12
+    ctx.close()
+    ctx_gen.close()
 
 
 def test_degenerate_shapes(capi, oracle):
