@@ -12,7 +12,7 @@ namespace ipxgpu {
 constexpr int kBandWarps = 31;   // consumer warps per CTA (+1 producer warp = 1024 threads)
 constexpr int kBandDepth = 4;    // rows per register batch
 constexpr int kBandVB = 8192;    // doubles per staged band (64 KB)
-constexpr size_t kBandSmemBudget = 227 * 1024 - 512;  // dynamic + the kernel's static part
+constexpr size_t kBandSmemBudget = 193 * 1024;  // 196 KB carve-out (incl. static + reserved part): a larger one leaves too little L1 for the loads in flight
 
 // Chooses the tiling for S segments gathering from a vector of length V.
 // Cost model, in bytes moved per item (one CTA): its share of the matrix

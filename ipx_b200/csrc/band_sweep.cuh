@@ -62,6 +62,7 @@ struct BandDev {
     double* partials = nullptr;      // [nparts * S] when nparts > 1
     long long rows = 0;
     int debug = 0;
+    unsigned long long* trace = nullptr;  // tuning only: [nitems][NW + 4] globaltimer stamps
 };
 
 struct BandHost {
@@ -94,6 +95,9 @@ __device__ __forceinline__ unsigned smem_u32(const void* p) {
 }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_inval(uint64_t* bar) {
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_fence_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -155,13 +159,13 @@ __device__ __forceinline__ double band_ld_f64(const void* p) {
     return v;
 }
 
+// One item (all threads of the CTA call it with the same arguments). Returns
+// this thread's share of the fused dot x'y (kBandRowFinal only). `smem_raw`
+// is the CTA's dynamic shared memory (band_smem_bytes(T.plan) bytes, 128-byte
+// aligned). The shared memory may be reused as soon as the call returns.
 template <int NW, int D, int DBG = 0, int LD = 0>
-__global__ void __launch_bounds__((NW + 1) * 32, 1)
-band_sweep_kernel(BandDev T, BandArgs A, int mode, Reduce red, CrState* st) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ double s_red[32];
-    __shared__ int s_flag;
-    if (st != nullptr && st->done) return;
+__device__ __forceinline__ double band_sweep_item(const BandDev& T, const BandArgs& A, int mode,
+                                                  int item, unsigned char* smem_raw) {
     const BandPlan& P = T.plan;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NBUF = P.NBUF;
@@ -173,8 +177,10 @@ band_sweep_kernel(BandDev T, BandArgs A, int mode, Reduce red, CrState* st) {
     double* v_buf = reinterpret_cast<double*>(smem_raw + 64 + rows_bytes);
     double* acc_s = v_buf + (size_t)NBUF * P.VB;
 
-    const int sb = blockIdx.x / P.nparts;
-    const int part = blockIdx.x - sb * P.nparts;
+    unsigned long long* trace = (DBG & 4) ? T.trace + (size_t)item * (NW + 4) : nullptr;
+    if ((DBG & 4) && tid == 0) trace[0] = globaltimer();
+    const int sb = item / P.nparts;
+    const int part = item - sb * P.nparts;
     const int seg_base = sb * P.SB;
     const int nseg = min(P.SB, P.S - seg_base);
     const int vb0 = part * P.K;
@@ -190,10 +196,11 @@ band_sweep_kernel(BandDev T, BandArgs A, int mode, Reduce red, CrState* st) {
     }
     for (int s = tid; s <= nseg; s += (NW + 1) * 32) acc_s[s] = 0.0;
     {
-        const int* src = T.row_ptr + (size_t)blockIdx.x * NW * (P.K + 1);
+        const int* src = T.row_ptr + (size_t)item * NW * (P.K + 1);
         for (int i = tid; i < NW * (P.K + 1); i += (NW + 1) * 32) s_rows[i] = src[i];
     }
     __syncthreads();
+    if ((DBG & 4) && tid == 0) trace[1] = globaltimer();
 
     if (warp == NW) {
         // ===== producer: stage the item's bands =====
@@ -296,29 +303,64 @@ band_sweep_kernel(BandDev T, BandArgs A, int mode, Reduce red, CrState* st) {
         // is in flight when the CTA exits) wait for the remaining bands
         while (k < nk - 1) advance(-1);
         if (DBG & 2) acc_s[lane] = sum;
+        if ((DBG & 4) && lane == 0) trace[4 + warp] = globaltimer();
     }
     __syncthreads();
+    if ((DBG & 4) && tid == 0) trace[2] = globaltimer();
 
     double dot = 0.0;
-    for (int s = tid; s < nseg; s += (NW + 1) * 32) {
-        const int g = seg_base + s;
-        const double a = acc_s[s];
+    {
+        // restrict: lets the (at most a handful of) iterations' loads go out together
+        const double* __restrict__ Wp = A.W;
+        const double* __restrict__ xp = A.x;
+        const double* __restrict__ Wsp = A.Ws;
+        double* __restrict__ outp = mode == kBandPartial ? T.partials + (size_t)part * P.S : A.out;
         if (mode == kBandColScale) {
-            A.out[g] = A.W ? __dmul_rn(a, A.W[g]) : a;
+#pragma unroll 4
+            for (int s = tid; s < nseg; s += (NW + 1) * 32) {
+                const int g = seg_base + s;
+                outp[g] = Wp ? __dmul_rn(acc_s[s], Wp[g]) : acc_s[s];
+            }
         } else if (mode == kBandRowFinal) {
-            const double xv = A.x[g];
-            const double yv = (A.Ws ? __dmul_rn(xv, A.Ws[g]) : 0.0) + a;
-            A.out[g] = yv;
-            dot += __dmul_rn(xv, yv);
+#pragma unroll 4
+            for (int s = tid; s < nseg; s += (NW + 1) * 32) {
+                const int g = seg_base + s;
+                const double xv = xp[g];
+                const double yv = (Wsp ? __dmul_rn(xv, Wsp[g]) : 0.0) + acc_s[s];
+                outp[g] = yv;
+                dot += __dmul_rn(xv, yv);
+            }
         } else {
-            T.partials[(size_t)part * P.S + g] = a;
+            for (int s = tid; s < nseg; s += (NW + 1) * 32) outp[seg_base + s] = acc_s[s];
         }
     }
+    if (tid == 0) {
+        for (int b = 0; b < NBUF; b++) {
+            mbar_inval(full + b);
+            mbar_inval(empty + b);
+        }
+    }
+    __syncthreads();
+    if ((DBG & 4) && tid == 0) trace[3] = globaltimer();
+    return dot;
+}
+
+template <int NW, int D, int DBG = 0, int LD = 0>
+__global__ void __launch_bounds__((NW + 1) * 32, 1)
+band_sweep_kernel(BandDev T, BandArgs A, int mode, Reduce red, CrState* st) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double s_red[32];
+    __shared__ int s_flag;
+    if (st != nullptr && st->done) return;
+    double dot = 0.0;
+    for (int item = blockIdx.x; item < T.plan.nitems; item += gridDim.x)
+        dot += band_sweep_item<NW, D, DBG, LD>(T, A, mode, item, smem_raw);
     if (mode == kBandRowFinal) {
         const double mine = block_sum(dot, s_red);
         double ts, ts2, tm;
-        if (grid_reduce(red, mine, 0.0, 0.0, s_red, &s_flag, &ts, &ts2, &tm) && tid == 0) {
-            A.out[P.S] = ts;
+        if (grid_reduce(red, mine, 0.0, 0.0, s_red, &s_flag, &ts, &ts2, &tm) &&
+            threadIdx.x == 0) {
+            A.out[T.plan.S] = ts;
             if (st) after_apply(st, A.apply_mode, ts, A.slot);
         }
     }

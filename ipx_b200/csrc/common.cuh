@@ -40,6 +40,8 @@ struct HostMirror {
     int done;
     int errflag;
     double resnorm;
+    int abort;  // written by the host: asks a persistent solve kernel to stop
+    int pad;
 };
 
 // Device-resident state of one CR solve. Written only by the finalising CTA of

@@ -153,6 +153,11 @@ struct ipxgpu_ctx {
     ipxgpu::BandDev* band1 = nullptr;  // t = W .* (A'x): gather x, segments = columns
     ipxgpu::BandDev* band2 = nullptr;  // y = A t: gather t, segments = rows
 
+    // persistent CR kernel (pcr_fused.cuh): grid barrier words and per-CTA partials
+    unsigned* fused_bar = nullptr;
+    double* fused_red = nullptr;
+    int fused_grid = 0;
+
     // L2 flush buffer for measurement helpers
     char* flush_buf = nullptr;
     size_t flush_bytes = 0;

@@ -14,6 +14,7 @@
 #include "spmv_kernels.cuh"
 #include "split.cuh"
 #include "band_plan.cuh"
+#include "pcr_fused.cuh"
 
 namespace ipxgpu {
 
@@ -271,6 +272,161 @@ static inline void cpu_relax() {
 #endif
 }
 
+// ---- persistent CR kernel (pcr_fused.cuh) ----
+
+static bool fused_available(ipxgpu_ctx* c) {
+    if (c->nranks != 1 || !c->band1 || !c->band2 || c->m <= 0) return false;
+    if (const char* env = std::getenv("IPXGPU_FUSED"))
+        if (std::atoi(env) == 0) return false;
+    return true;
+}
+
+static int run_cr_fused(ipxgpu_ctx* c, bool precond, bool zero_start, bool use_resscale,
+                        double tol, int64_t maxiter, ipxgpu_cr_result* result,
+                        ipxgpu_interrupt_fn interrupt, void* user, int64_t hist_cap) {
+    const int m = (int)c->m;
+    const char* trace_env = std::getenv("IPXGPU_FUSED_TRACE");
+    const bool item_trace = trace_env && std::atoi(trace_env) == 2;
+    auto kernel = item_trace ? pcr_fused_kernel<kBandWarps, kBandDepth, 4>
+                             : pcr_fused_kernel<kBandWarps, kBandDepth, 0>;
+    const size_t smem = std::max(c->band1->plan.smem, c->band2->plan.smem);
+    const int threads = (kBandWarps + 1) * 32;
+    IPXGPU_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)kBandSmemBudget));
+    if (c->fused_grid == 0) {
+        int per_sm = 0;
+        IPXGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+        if (per_sm < 1) return fail(IPXGPU_ERR_STATE, "persistent CR kernel does not fit an SM");
+        c->fused_grid = c->num_sms;  // one CTA per SM (shared memory bound)
+        IPXGPU_TRY(dev_alloc(&c->fused_bar, 1));
+        IPXGPU_TRY(dev_alloc(&c->fused_red, (size_t)kFusedStages * 3 * c->fused_grid + 1));
+    }
+    if (!c->band2->partials)
+        IPXGPU_TRY(dev_alloc(&c->band2->partials, (size_t)c->band2->plan.nparts * m));
+
+    CrState h;
+    std::memset(&h, 0, sizeof h);
+    h.tol = tol;
+    h.maxiter = maxiter;
+    h.precond = precond ? 1 : 0;
+    h.hist = hist_cap > 0 ? c->v_hist : nullptr;
+    h.hist_cap = hist_cap;
+    h.mirror = c->mirror_dev;
+    c->mirror_host->iter = 0;
+    c->mirror_host->done = 0;
+    c->mirror_host->errflag = 0;
+    c->mirror_host->resnorm = 0.0;
+    c->mirror_host->abort = 0;
+    IPXGPU_CUDA(cudaMemcpyAsync(c->st_dev, &h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+    IPXGPU_CUDA(cudaMemsetAsync(c->fused_red + (size_t)kFusedStages * 3 * c->fused_grid, 0,
+                                sizeof(double), c->stream));
+    IPXGPU_CUDA(cudaMemsetAsync(c->fused_bar, 0, sizeof(unsigned), c->stream));
+    if (zero_start) IPXGPU_CUDA(cudaMemsetAsync(c->v_y, 0, sizeof(double) * m, c->stream));
+
+    FusedArgs F;
+    F.T1 = *c->band1;
+    F.T2 = *c->band2;
+    F.v.m = m;
+    F.v.y = c->v_y;
+    F.v.r = c->v_r;
+    F.v.s = c->v_s;
+    F.v.p = c->v_p;
+    F.v.Cp = c->v_Cp;
+    F.v.Cs = c->v_Cs;
+    F.v.q = c->v_q;
+    F.v.diag = c->diag;
+    F.v.resscale = use_resscale ? c->v_resscale : nullptr;
+    F.rhs = c->v_rhs;
+    F.Wc = c->Wc;
+    F.Ws = c->Ws;
+    F.t = c->t;
+    F.zero_start = zero_start ? 1 : 0;
+    F.sync = GridSync{c->fused_bar, c->fused_red};
+    F.abort_word = c->fused_red + (size_t)kFusedStages * 3 * c->fused_grid;
+    F.st = c->st_dev;
+    F.abort_flag = &c->mirror_dev->abort;
+    F.trace = nullptr;
+    F.trace_cap = 0;
+    const bool tracing = trace_env != nullptr;
+    const int NWp = kBandWarps + 4;
+    if (item_trace) {
+        IPXGPU_TRY(dev_alloc(&F.T1.trace, (size_t)F.T1.plan.nitems * NWp));
+        IPXGPU_TRY(dev_alloc(&F.T2.trace, (size_t)F.T2.plan.nitems * NWp));
+    }
+    if (tracing) {
+        F.trace_cap = 4096;
+        IPXGPU_TRY(dev_alloc(&F.trace, (size_t)F.trace_cap));
+        IPXGPU_CUDA(cudaMemsetAsync(F.trace, 0, 8 * (size_t)F.trace_cap, c->stream));
+    }
+    void* args[] = {&F};
+    IPXGPU_CUDA(cudaLaunchCooperativeKernel((void*)kernel, dim3(c->fused_grid), dim3(threads), args,
+                                            smem, c->stream));
+    c->launches++;
+
+    int64_t interrupted = 0;
+    if (interrupt) {
+        // The kernel polls mirror->abort; the host polls the caller's interrupt check.
+        for (;;) {
+            cudaError_t q = cudaStreamQuery(c->stream);
+            if (q == cudaSuccess) break;
+            if (q != cudaErrorNotReady)
+                return fail(IPXGPU_ERR_CUDA, std::string("CR kernel: ") + cudaGetErrorString(q));
+            if (!interrupted && (interrupted = interrupt(user)) != 0) c->mirror_host->abort = 1;
+            cpu_relax();
+        }
+    }
+    IPXGPU_CUDA(cudaStreamSynchronize(c->stream));
+    IPXGPU_CUDA(cudaMemcpy(&h, c->st_dev, sizeof h, cudaMemcpyDeviceToHost));
+    if (tracing) {
+        // CTA 0, 10 stamps per iteration after the initialisation:
+        // dir | dir sync | upd | upd sync | s1 | s1 sync | s2 | s2 sync | comb | comb sync
+        std::vector<unsigned long long> tr((size_t)F.trace_cap);
+        cudaMemcpy(tr.data(), F.trace, 8 * tr.size(), cudaMemcpyDeviceToHost);
+        int n = 0;
+        while (n < F.trace_cap && tr[n]) n++;
+        fprintf(stderr, "[fused trace] %d stamps; deltas (us):", n);
+        for (int k = 1; k < n && k < 80; k++) fprintf(stderr, " %.2f", (tr[k] - tr[k - 1]) / 1e3);
+        fprintf(stderr, "\n");
+        cudaFree(F.trace);
+    }
+    if (item_trace) {
+        // per-item stamps of the LAST apply: start | prologue end | warps done | end | warp ends
+        for (int sw = 1; sw <= 2; sw++) {
+            const BandDev& T = sw == 1 ? F.T1 : F.T2;
+            const int ni = T.plan.nitems;
+            std::vector<unsigned long long> tr((size_t)ni * NWp);
+            cudaMemcpy(tr.data(), T.trace, 8 * tr.size(), cudaMemcpyDeviceToHost);
+            unsigned long long t0 = ~0ull;
+            for (int i = 0; i < ni; i++) t0 = std::min(t0, tr[(size_t)i * NWp]);
+            const char* names[4] = {"start (rel)", "prologue", "main", "epilogue"};
+            for (int q = 0; q < 4; q++) {
+                double mn = 1e30, mx = 0, sum = 0;
+                for (int i = 0; i < ni; i++) {
+                    const unsigned long long* r = tr.data() + (size_t)i * NWp;
+                    const double v = q == 0 ? (double)(r[0] - t0) : (double)(r[q] - r[q - 1]);
+                    mn = std::min(mn, v);
+                    mx = std::max(mx, v);
+                    sum += v;
+                }
+                fprintf(stderr, "[fused item trace] sweep %d %-12s min %6.2f mean %6.2f max %6.2f us\n",
+                        sw, names[q], mn / 1e3, sum / ni / 1e3, mx / 1e3);
+            }
+            cudaFree(T.trace);
+        }
+    }
+    if (result) {
+        result->errflag = interrupted ? interrupted : h.errflag;
+        result->iter = h.iter;
+        result->time_op = 1e-9 * (double)h.t_op;
+        result->time_pre = 1e-9 * (double)h.t_pre;
+        result->time_B = 0.0;
+        result->time_Bt = 0.0;
+        result->time_NNt = 0.0;
+        result->resnorm = h.resnorm;
+    }
+    return IPXGPU_OK;
+}
+
 // Device-resident CR driver. Vectors v_rhs, v_y (initial iterate, only if
 // !zero_start), v_resscale (if use_resscale) must be on the device already.
 static int run_cr(ipxgpu_ctx* c, int op, bool precond, bool zero_start, bool use_resscale,
@@ -278,6 +434,9 @@ static int run_cr(ipxgpu_ctx* c, int op, bool precond, bool zero_start, bool use
                   ipxgpu_interrupt_fn interrupt, void* user, int64_t hist_cap) {
     const int m = (int)c->m;
     if (maxiter < 0) maxiter = c->m + 100;
+    if (op == 0 && fused_available(c))
+        return run_cr_fused(c, precond, zero_start, use_resscale, tol, maxiter, result, interrupt,
+                            user, hist_cap);
     const int grid = grid_for(c, m);
     IPXGPU_TRY(ensure_reduce(c, grid));
 
@@ -442,6 +601,8 @@ void ipxgpu_destroy(ipxgpu_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     destroy_split(c);
+    dev_free(c->fused_bar);
+    dev_free(c->fused_red);
     if (c->band1) { free_band(c->band1); delete c->band1; }
     if (c->band2) { free_band(c->band2); delete c->band2; }
     free_matrix(&c->csc);

@@ -1,0 +1,369 @@
+// The whole (preconditioned) Conjugate Residuals solve with C = A*W*A' as ONE
+// persistent cooperative kernel (reference src/conjugate_residuals.cc:14-88,
+// :90-213 with C = NormalMatrix, P = DiagonalPrecond).
+//
+// The launch-per-stage loop of cr_kernels.cuh pays ~7-10 us of launch, fill
+// and drain per kernel, 5 kernels per CR iteration, against ~40 us of memory
+// traffic. Here one CTA per SM stays resident for the whole solve and the
+// stages of an iteration are separated by grid barriers:
+//
+//   update     y += a p; r -= a Cp; [s -= a q]      own slice of the m-vectors
+//   -- barrier (s complete: sweep 1 gathers it)
+//   sweep 1    t = W .* (A' s)                      banded items over columns
+//   -- barrier
+//   sweep 2    partial[part] = A[:, part] t         banded items over rows
+//   -- barrier
+//   combine    Cs = Ws .* s + sum(partials); dot    own slice
+//   -- barrier (dot -> beta)
+//   direction  p = s + b p; Cp = Cs + b Cp; [q = Cp./diag]; pdot; [s = r./diag]
+//   -- barrier (pdot, resnorm -> tests, alpha)
+//
+// Every CTA owns a fixed slice of the m-vectors and reduces the per-CTA
+// partials of a stage in CTA order while it waits at the barrier, so all CTAs hold
+// identical scalars and take identical decisions; results are run-to-run
+// deterministic. The scalar logic is the reference's, in its order.
+#pragma once
+
+#include "band_sweep.cuh"
+#include "cr_kernels.cuh"
+
+namespace ipxgpu {
+
+// Grid-wide synchronisation of the cooperative grid: one monotonically
+// increasing arrival counter (never reset: the k-th barrier completes when it
+// reaches k * gridDim.x) and, per stage, an array of per-CTA values that every
+// CTA reduces in CTA order after the barrier, so all CTAs obtain identical
+// results.
+struct GridSync {
+    unsigned* count;  // arrival counter, zero before the launch
+    double* vals;     // [kFusedStages][3][gridDim.x]
+};
+
+struct FusedArgs {
+    BandDev T1, T2;
+    CrVectors v;
+    const double* rhs;
+    const double* Wc;   // structural weights or nullptr (1)
+    const double* Ws;   // slack weights or nullptr (0)
+    double* t;          // intermediate n-vector
+    int zero_start;
+    GridSync sync;
+    double* abort_word; // set nonzero by CTA 0 when the host asked to stop
+    CrState* st;
+    const volatile int* abort_flag;  // host-mapped; nonzero asks the solve to stop
+    unsigned long long* trace;       // tuning only: globaltimer of CTA 0 at every stage end
+    int trace_cap;
+};
+
+constexpr int kFusedStages = 6;
+enum FusedStage : int { kStSweep1 = 0, kStSweep2, kStCombine, kStInit, kStDirection, kStUpdate };
+
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+// Arrives at barrier number `gen` (1, 2, ...) and waits for it. Generic-proxy
+// writes of any CTA before its arrival are visible to generic and bulk-copy
+// reads of every CTA after the wait. With stage >= 0, thread 0's (v0, v1, v2)
+// are published and the sums / sum / max over all CTAs are returned to all
+// threads.
+__device__ __forceinline__ void grid_sync(const GridSync& g, unsigned gen, int stage, double v0,
+                                          double v1, double v2, double* s_bcast, double* out0,
+                                          double* out1, double* out2) {
+    const int nblk = gridDim.x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (stage >= 0) {
+            double* base = g.vals + (size_t)stage * 3 * nblk;
+            base[blockIdx.x] = v0;
+            base[nblk + blockIdx.x] = v1;
+            base[2 * nblk + blockIdx.x] = v2;
+        }
+        // Global memory is coherent in L2 for both proxies; the proxy fences of
+        // thread 0 order its release / acquire against the bulk copies that
+        // read what other CTAs wrote before the barrier.
+        fence_proxy_async();
+        __threadfence();
+        asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(g.count) : "memory");
+        const unsigned target = gen * (unsigned)nblk;
+        unsigned now;
+        do {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(g.count) : "memory");
+        } while ((int)(now - target) < 0);
+        __threadfence();  // acquire; also drops this SM's stale L1 lines
+        fence_proxy_async();
+    }
+    __syncthreads();
+    if (stage >= 0) {
+        if (threadIdx.x < 32) {
+            const double* base = g.vals + (size_t)stage * 3 * nblk;
+            double s = 0.0, s2 = 0.0, mx = 0.0;
+            for (int b = threadIdx.x; b < nblk; b += 32) {
+                s += __ldcg(base + b);
+                s2 += __ldcg(base + nblk + b);
+                mx = fmax(mx, __ldcg(base + 2 * nblk + b));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s += __shfl_down_sync(0xffffffffu, s, o);
+                s2 += __shfl_down_sync(0xffffffffu, s2, o);
+                mx = fmax(mx, __shfl_down_sync(0xffffffffu, mx, o));
+            }
+            if (threadIdx.x == 0) {
+                s_bcast[0] = s;
+                s_bcast[1] = s2;
+                s_bcast[2] = mx;
+            }
+        }
+        __syncthreads();
+        *out0 = s_bcast[0];
+        *out1 = s_bcast[1];
+        *out2 = s_bcast[2];
+    }
+}
+
+// CTA-wide sum, sum, max in one pass; valid in thread 0. s_red: 96 doubles.
+__device__ __forceinline__ void fused_block_reduce(double* s_red, double& a, double& b, double& c) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_down_sync(0xffffffffu, a, o);
+        b += __shfl_down_sync(0xffffffffu, b, o);
+        c = fmax(c, __shfl_down_sync(0xffffffffu, c, o));
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) {
+        s_red[warp] = a;
+        s_red[32 + warp] = b;
+        s_red[64 + warp] = c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        a = s_red[0];
+        b = s_red[32];
+        c = s_red[64];
+        for (int w = 1; w < nw; w++) {
+            a += s_red[w];
+            b += s_red[32 + w];
+            c = fmax(c, s_red[64 + w]);
+        }
+    }
+}
+
+template <int NW, int D, int DBG = 0>
+__global__ void __launch_bounds__((NW + 1) * 32, 1)
+pcr_fused_kernel(FusedArgs F) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double s_red[96];
+    __shared__ double s_bcast[4];
+    __shared__ CrState s_st;   // this CTA's replica of the solve state
+
+    const int tid = threadIdx.x;
+    const int nthr = (NW + 1) * 32;
+    const CrVectors& v = F.v;
+    const int m = v.m;
+    const int chunk = (m + gridDim.x - 1) / gridDim.x;
+    const int i0 = min(m, (int)blockIdx.x * chunk), i1 = min(m, i0 + chunk);
+    const bool lead = blockIdx.x == 0 && tid == 0;
+
+    if (tid == 0) {
+        s_st = *F.st;
+        s_st.t_last = globaltimer();
+    }
+    __syncthreads();
+    const bool precond = s_st.precond != 0;
+
+    auto stamp_lead = [&](int slot) {
+        if (lead) stamp(&s_st, slot);
+    };
+    int ntrace = 0;
+    auto trace = [&]() {
+        if (lead && F.trace && ntrace < F.trace_cap) F.trace[ntrace++] = globaltimer();
+    };
+    unsigned gen = 0;  // barriers passed so far (identical in all CTAs)
+    double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+    // Barrier with reduction; (a, b, c) are this thread's shares of sum, sum,
+    // max. Totals land in r0, r1, r2 of every thread.
+    auto sync_stage = [&](int stage, double a, double b, double c2) {
+        fused_block_reduce(s_red, a, b, c2);
+        trace();
+        grid_sync(F.sync, ++gen, stage, a, b, c2, s_bcast, &r0, &r1, &r2);
+        trace();
+    };
+    auto sync_plain = [&]() {
+        trace();
+        grid_sync(F.sync, ++gen, -1, 0.0, 0.0, 0.0, s_bcast, &r0, &r1, &r2);
+        trace();
+    };
+
+    // lhs (own m-slice) = A W A' x; returns the total x'lhs to all threads.
+    auto apply = [&](const double* x, double* lhs) -> double {
+        BandArgs a1{x, F.Wc, nullptr, nullptr, F.t, kApplyPlain, kSlotNone};
+        for (int item = blockIdx.x; item < F.T1.plan.nitems; item += gridDim.x)
+            band_sweep_item<NW, D, DBG>(F.T1, a1, kBandColScale, item, smem_raw);
+        sync_plain();
+        BandArgs a2{F.t, nullptr, nullptr, nullptr, nullptr, kApplyPlain, kSlotNone};
+        for (int item = blockIdx.x; item < F.T2.plan.nitems; item += gridDim.x)
+            band_sweep_item<NW, D, DBG>(F.T2, a2, kBandPartial, item, smem_raw);
+        sync_plain();
+        const int nparts = F.T2.plan.nparts;
+        double dot = 0.0;
+        for (int i = i0 + tid; i < i1; i += nthr) {
+            double acc = 0.0;
+#pragma unroll 8
+            for (int p = 0; p < nparts; p++) acc += __ldcg(F.T2.partials + (size_t)p * m + i);
+            const double xv = x[i];
+            const double yv = (F.Ws ? __dmul_rn(xv, F.Ws[i]) : 0.0) + acc;
+            lhs[i] = yv;
+            dot += __dmul_rn(xv, yv);
+        }
+        sync_stage(kStCombine, dot, 0.0, 0.0);
+        stamp_lead(kSlotOp);
+        return r0;
+    };
+
+    // ---- initialisation (reference :33-40, :118-127) ----
+    if (!F.zero_start) {
+        apply(v.y, v.Cs);  // own slice of C*y, read back by the same threads below
+    }
+    {
+        double rs = 0.0, mx = 0.0;
+        for (int i = i0 + tid; i < i1; i += nthr) {
+            const double ri = F.zero_start ? F.rhs[i] : F.rhs[i] - v.Cs[i];
+            v.r[i] = ri;
+            v.p[i] = 0.0;
+            v.Cp[i] = 0.0;
+            if (precond) {
+                const double si = ri / v.diag[i];
+                v.s[i] = si;
+                rs += __dmul_rn(si, ri);
+            }
+            const double sc = v.resscale ? __dmul_rn(v.resscale[i], ri) : ri;
+            mx = fmax(mx, fabs(sc));
+        }
+        sync_stage(kStInit, rs, 0.0, mx);
+        if (tid == 0) {
+            s_st.rsdot_prev = r0;
+            s_st.resnorm = r2;
+        }
+        stamp_lead(precond ? kSlotPre : kSlotVec);
+        __syncthreads();
+    }
+    const double* sv = precond ? v.s : v.r;
+    {
+        const double dot = apply(sv, v.Cs);
+        if (tid == 0) {
+            s_st.cdot = dot;
+            s_st.beta = 0.0;
+        }
+        __syncthreads();
+    }
+
+    for (;;) {
+        // ---- direction (reference :79-80 / :181-207) and the tests at the top
+        //      of the next pass (:50-71 / :137-172) ----
+        const double beta = s_st.beta;
+        const long long iter = s_st.iter;
+        const bool recompute = precond && iter > 0 && (iter % 5 == 0);
+        double pd = 0.0, rs = 0.0;
+        for (int i = i0 + tid; i < i1; i += nthr) {
+            const double pn = sv[i] + __dmul_rn(beta, v.p[i]);
+            const double cpn = v.Cs[i] + __dmul_rn(beta, v.Cp[i]);
+            v.p[i] = pn;
+            v.Cp[i] = cpn;
+            if (precond) {
+                const double d = v.diag[i];
+                const double qi = cpn / d;
+                v.q[i] = qi;
+                pd += __dmul_rn(qi, cpn);
+                if (recompute) {
+                    const double ri = v.r[i];
+                    const double sn = ri / d;
+                    v.s[i] = sn;
+                    rs += __dmul_rn(sn, ri);
+                }
+            } else {
+                pd += __dmul_rn(cpn, cpn);
+            }
+        }
+        if (lead && (iter & 3) == 0 && F.abort_flag && *F.abort_flag) *F.abort_word = 1.0;
+        sync_stage(kStDirection, pd, rs, 0.0);
+        const double tpd = r0, trs = r1;
+        const bool aborted = __ldcg(F.abort_word) != 0.0;
+        if (tid == 0) {
+            int done = 0, err = 0;
+            if (recompute) {
+                if (trs >= s_st.rsdot_prev) {
+                    err = 204;
+                    done = 1;
+                } else {
+                    s_st.rsdot_prev = trs;
+                }
+            }
+            if (!done) {
+                const double resnorm = s_st.resnorm;
+                if (lead && s_st.hist && iter < s_st.hist_cap) s_st.hist[iter] = resnorm;
+                s_st.pdot = tpd;
+                if (resnorm <= s_st.tol) {
+                    done = 1;
+                } else if (iter == s_st.maxiter) {
+                    err = 201;
+                    done = 1;
+                } else if (s_st.cdot <= 0.0) {
+                    err = 202;
+                    done = 1;
+                } else if (precond && tpd <= 0.0) {
+                    err = 203;
+                    done = 1;
+                } else {
+                    const double alpha = s_st.cdot / tpd;
+                    if (!isfinite(alpha)) {
+                        err = 205;
+                        done = 1;
+                    }
+                    s_st.alpha = alpha;
+                }
+            }
+            if (aborted) done = 1;
+            s_st.errflag = err;
+            s_st.done = done;
+            if (lead) stamp(&s_st, precond ? kSlotPre : kSlotVec);
+        }
+        __syncthreads();
+        if (s_st.done) break;
+
+        // ---- update (reference :72-73 / :173-175) ----
+        {
+            const double alpha = s_st.alpha;
+            double mx = 0.0;
+            for (int i = i0 + tid; i < i1; i += nthr) {
+                v.y[i] = v.y[i] + __dmul_rn(alpha, v.p[i]);
+                const double ri = v.r[i] - __dmul_rn(alpha, v.Cp[i]);
+                v.r[i] = ri;
+                if (precond) v.s[i] = v.s[i] - __dmul_rn(alpha, v.q[i]);
+                const double sc = v.resscale ? __dmul_rn(v.resscale[i], ri) : ri;
+                mx = fmax(mx, fabs(sc));
+            }
+            sync_stage(kStUpdate, 0.0, 0.0, mx);
+            if (tid == 0) s_st.resnorm = r2;
+            stamp_lead(kSlotVec);
+        }
+        // ---- C.Apply and its scalar step (reference :75-81 / :176-184) ----
+        {
+            const double dot = apply(sv, v.Cs);
+            if (tid == 0) {
+                s_st.beta = dot / s_st.cdot;
+                s_st.cdot = dot;
+                s_st.iter += 1;
+            }
+            __syncthreads();
+        }
+    }
+
+    if (lead) {
+        *F.st = s_st;
+        publish(F.st);
+    }
+}
+
+}  // namespace ipxgpu

@@ -96,6 +96,7 @@ static KernelFn pick_reg(int dbg) {
         case 0: return band_sweep_kernel<NW, D, 0, LD>;
         case 1: return band_sweep_kernel<NW, D, 1, LD>;
         case 2: return band_sweep_kernel<NW, D, 2, LD>;
+        case 4: return band_sweep_kernel<NW, D, 4, LD>;
         default: return band_sweep_kernel<NW, D, 3, LD>;
     }
 }
@@ -109,7 +110,8 @@ static KernelFn pick(const Cfg& c, int dbg) {
 }
 
 static size_t cfg_smem(const Cfg& c, const BandPlan& P) {
-    return P.smem;
+    static const size_t extra = getenv("BSWEEP_EXTRA_SMEM") ? atoi(getenv("BSWEEP_EXTRA_SMEM")) : 0;
+    return P.smem + extra;
 }
 
 static void launch_any(const Cfg& c, const BandDev& T, const BandArgs& A, int mode, Reduce red,
@@ -405,6 +407,58 @@ int main(int argc, char** argv) {
             for (int i = 0; i < m; i++) e = std::max(e, std::fabs(out[i] - y_ref[i]));
             printf("    apply relerr %.2e\n", e / ymax);
             for (auto& e2 : ev) CK(cudaEventDestroy(e2));
+        }
+        if (getenv("BSWEEP_TRACE")) {
+            for (int sweep = 1; sweep <= 2; sweep++) {
+                BandDev& T = Ts[sweep];
+                const int NWp = c.NW + 4, ni = T.plan.nitems;
+                CK(cudaMalloc(&T.trace, (size_t)ni * NWp * 8));
+                CK(cudaMemset(T.trace, 0, (size_t)ni * NWp * 8));
+                T.debug = 4;
+                for (int w = 0; w < 3; w++) {
+                    run_sweep(sweep == 1 ? 2 : 1);  // evict this sweep's stream from L2
+                    CK(cudaStreamSynchronize(s));
+                    Ts[3 - sweep].debug = 0;
+                    run_sweep(sweep);
+                }
+                CK(cudaStreamSynchronize(s));
+                std::vector<unsigned long long> tr((size_t)ni * NWp);
+                CK(cudaMemcpy(tr.data(), T.trace, tr.size() * 8, cudaMemcpyDeviceToHost));
+                unsigned long long t0 = ~0ull, t3 = 0;
+                for (int i = 0; i < ni; i++) {
+                    t0 = std::min(t0, tr[(size_t)i * NWp]);
+                    t3 = std::max(t3, tr[(size_t)i * NWp + 3]);
+                }
+                auto stats = [&](auto&& get, const char* name) {
+                    double mn = 1e30, mx = 0, sum = 0;
+                    for (int i = 0; i < ni; i++) {
+                        const double v = get(i);
+                        mn = std::min(mn, v);
+                        mx = std::max(mx, v);
+                        sum += v;
+                    }
+                    printf("      %-28s min %7.2f  mean %7.2f  max %7.2f us\n", name, mn / 1e3,
+                           sum / ni / 1e3, mx / 1e3);
+                };
+                printf("    TRACE sweep %d: first start -> last end %.2f us\n", sweep,
+                       (t3 - t0) / 1e3);
+                stats([&](int i) { return (double)(tr[(size_t)i * NWp] - t0); }, "item start (rel)");
+                stats([&](int i) { return (double)(tr[(size_t)i * NWp + 1] - tr[(size_t)i * NWp]); },
+                      "prologue");
+                stats([&](int i) {
+                    unsigned long long e = ~0ull;
+                    for (int w = 0; w < c.NW; w++) e = std::min(e, tr[(size_t)i * NWp + 4 + w]);
+                    return (double)(e - tr[(size_t)i * NWp + 1]);
+                }, "first warp done");
+                stats([&](int i) { return (double)(tr[(size_t)i * NWp + 2] - tr[(size_t)i * NWp + 1]); },
+                      "all warps done");
+                stats([&](int i) { return (double)(tr[(size_t)i * NWp + 3] - tr[(size_t)i * NWp + 2]); },
+                      "epilogue");
+                stats([&](int i) { return (double)(tr[(size_t)i * NWp + 3] - t0); }, "item end (rel)");
+                T.debug = 0;
+                CK(cudaFree(T.trace));
+                T.trace = nullptr;
+            }
         }
         for (int sweep = 1; sweep <= 2; sweep++) {
             CK(cudaFree(Ts[sweep].row_ptr));
