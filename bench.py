@@ -42,7 +42,7 @@ M_ROWS = 100_000
 N_COLS = 1_000_000
 NNZ_PER_COL = 10
 SEED = 1002
-NCU_TRAFFIC_BYTES_PER_APPLY = 271_440_000  # see roofline.traffic below
+NCU_TRAFFIC_BYTES_PER_APPLY = 297_520_000  # see roofline.traffic below
 
 
 def algorithmic_bytes(m, n, nnzA):
@@ -311,13 +311,17 @@ def run_gpu(args):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
-                         # dram__bytes_read+write of sweep 1 + sweep 2 per apply, from the
-                         # ncu --set full capture profiles/r01_ncu_full_sweeps_c2.csv
-                         # (137.4 MB + 134.0 MB); only valid for the 1-GPU C2 workload.
+                         # dram__bytes_read+write of one pcr_fused_kernel launch (a CR solve of
+                         # 6 iterations = 7 applies: 2051.9 MB read + 30.7 MB written) / 7, from
+                         # the ncu --set full capture profiles/r01b_ncu_full_band_fused.csv;
+                         # only valid for the 1-GPU C2 workload.
                          "traffic": NCU_TRAFFIC_BYTES_PER_APPLY if world == 1 else None,
-                         "traffic_source": "profiles/r01_ncu_full_sweeps_c2.csv",
+                         "traffic_source": "profiles/r01b_ncu_full_band_fused.csv",
                          "peak_source": peak_src,
-                         "kernel": "seg_sweep_kernel<OpColDotScale> + seg_sweep_kernel<OpRowGather>",
+                         "kernel": ("pcr_fused_kernel (persistent CR solve): banded sweep 1 + sweep 2 "
+                                    "+ combine stages of one A*D^2*A' apply") if world == 1 else
+                                   "band_sweep_kernel (sweep 1) + band_sweep_kernel (sweep 2) + "
+                                   "band_combine_kernel",
                          "algorithmic_bytes_per_apply": bytes_apply,
                          "apply_us_in_loop": 1e6 * t_apply,
                          "apply_us_isolated_l2_flushed": 1e3 * iso["apply_ms"] if iso else None,

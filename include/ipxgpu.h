@@ -224,6 +224,15 @@ int ipxgpu_split_apply(ipxgpu_ctx* ctx, const double* rhs, double* lhs,
  * (A'x), sweep2 (A t)]. */
 int ipxgpu_time_normal_apply(ipxgpu_ctx* ctx, int reps, int flush_l2,
                              double out_ms[3]);
+/* Host-only check of the banded sweep layout (no device needed): re-tiles the
+ * structural columns of AI for both sweeps of the normal-matrix apply with the
+ * planner's choice (force != 0: accept any plan that fits), walks the row
+ * streams on the host exactly as the kernel does and compares
+ * t = A'x and y = A t with a plain CSC computation. out = [sweep-1 planned,
+ * sweep-1 max abs error, sweep-1 padding fraction, sweep-2 planned, sweep-2
+ * max abs error, sweep-2 padding fraction]. */
+int ipxgpu_band_selftest(int64_t m, int64_t n, const int64_t* AIp, const int64_t* AIi,
+                         const double* AIx, const double* x, int32_t force, double out[6]);
 /* Number of kernels launched by this context since creation. */
 int ipxgpu_launch_count(ipxgpu_ctx* ctx, int64_t* count);
 

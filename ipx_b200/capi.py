@@ -40,7 +40,7 @@ EXPORTS = ("ipxgpu_default_options ipxgpu_last_error ipxgpu_device_count ipxgpu_
            "ipxgpu_normal_apply_dev ipxgpu_diag_factorize ipxgpu_diag_get ipxgpu_diag_set "
            "ipxgpu_diag_apply ipxgpu_pcr_solve ipxgpu_pcr_solve_dev ipxgpu_cr_solve ipxgpu_kktdiag_factorize "
            "ipxgpu_kktdiag_solve ipxgpu_lu_load ipxgpu_tri_solve ipxgpu_split_prepare "
-           "ipxgpu_split_apply ipxgpu_time_normal_apply ipxgpu_launch_count").split()
+           "ipxgpu_split_apply ipxgpu_time_normal_apply ipxgpu_launch_count ipxgpu_band_selftest").split()
 
 _lib = None
 
@@ -68,6 +68,22 @@ def load():
 def _check(rc):
     if rc != 0:
         raise IpxGpuError(rc, load().ipxgpu_last_error().decode())
+
+
+def band_selftest(m, n, AIp, AIi, AIx, x, force=False):
+    """Host-only check of the banded sweep layout (ipxgpu_band_selftest); no device needed."""
+    import numpy as np
+    AIp = np.ascontiguousarray(AIp, dtype=np.int64)
+    AIi = np.ascontiguousarray(AIi, dtype=np.int64)
+    AIx = np.ascontiguousarray(AIx, dtype=np.float64)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = (C.c_double * 6)()
+    _check(load().ipxgpu_band_selftest(
+        i64(m), i64(n), AIp.ctypes.data_as(C.POINTER(i64)), AIi.ctypes.data_as(C.POINTER(i64)),
+        AIx.ctypes.data_as(C.POINTER(C.c_double)), x.ctypes.data_as(C.POINTER(C.c_double)),
+        C.c_int32(1 if force else 0), out))
+    keys = "planned err pad".split()
+    return {"sweep1": dict(zip(keys, list(out)[:3])), "sweep2": dict(zip(keys, list(out)[3:]))}
 
 
 def _d(a):

@@ -51,7 +51,9 @@ static bool plan_band(BandPlan* out, int V, int S, long long nnz, int num_sms, d
             const int waves = (P.nitems + num_sms - 1) / num_sms;
             const double staged = 8.0 * (double)P.K * VB;
             const double partial = P.nparts > 1 ? 24.0 * P.SB : 0.0;
-            const double per_item = stream / P.nitems + 0.5 * staged + partial;
+            // the largest item: K bands of SB segments (the last part / block are smaller)
+            const double share = std::min(1.0, (double)P.K * VB / V) * ((double)P.SB / S);
+            const double per_item = stream * share + 0.5 * staged + partial;
             const double cost = waves * per_item;
             if (best_cost < 0.0 || cost < best_cost) {
                 best_cost = cost;

@@ -123,13 +123,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
             : "memory");
     } while (!ok);
 }
+// Bulk copy global -> shared with an L2 eviction policy: the gathered vector is
+// re-read by every CTA while the matrix streams through L2, so it is kept with
+// evict_last priority.
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes,
-                                         uint64_t* bar) {
+                                         uint64_t* bar, uint64_t policy) {
     asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-            "r"(smem_u32(dst)),
-        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint "
+        "[%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
         : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 
 // ---- kernel ----
@@ -207,6 +215,7 @@ __device__ __forceinline__ double band_sweep_item(const BandDev& T, const BandAr
         if (lane == 0 && !(DBG & 1)) {
             int b = 0;
             unsigned par = 1;  // parity of the previous use of buffer b
+            const uint64_t keep = policy_evict_last();
             for (int k = 0; k < nk; k++) {
                 if (k >= NBUF) mbar_wait(empty + b, par);
                 int r = k + rot;
@@ -222,7 +231,7 @@ __device__ __forceinline__ double band_sweep_item(const BandDev& T, const BandAr
                     const unsigned n = min(16384u, bytes - off);
                     bulk_g2s(reinterpret_cast<unsigned char*>(dst) + off,
                              reinterpret_cast<const unsigned char*>(A.v + vbase) + off, n,
-                             full + b);
+                             full + b, keep);
                 }
                 if (++b == NBUF) {
                     b = 0;

@@ -1228,6 +1228,103 @@ int ipxgpu_kktdiag_solve(ipxgpu_ctx* c, const double* a, const double* b, double
     return IPXGPU_OK;
 }
 
+// ---- host-only layout check ----
+
+// Walks the row streams of a banded layout as band_sweep_kernel does.
+static void band_emulate(const BandPlan& P, const BandHost& H, const double* v,
+                         std::vector<double>* out) {
+    out->assign((size_t)P.S, 0.0);
+    std::vector<double> acc((size_t)P.SB + 1);
+    for (int sb = 0; sb < P.NSB; sb++)
+        for (int part = 0; part < P.nparts; part++) {
+            const int item = sb * P.nparts + part;
+            const int vb0 = part * P.K;
+            const int nk = std::min(P.NVB, vb0 + P.K) - vb0;
+            const int rot = sb % nk;
+            std::fill(acc.begin(), acc.end(), 0.0);
+            for (int w = 0; w < P.NW; w++) {
+                const int* rp = H.row_ptr.data() + ((size_t)item * P.NW + w) * (P.K + 1);
+                for (int l = 0; l < 32; l++) {
+                    double sum = 0.0;
+                    for (int k = 0; k < nk; k++) {
+                        int r = k + rot;
+                        if (r >= nk) r -= nk;
+                        const int vbase = (vb0 + r) * P.VB;
+                        for (int row = rp[k]; row < rp[k + 1]; row++) {
+                            const uint32_t* R = H.stream.data() + (size_t)row * 96;
+                            const uint32_t key = R[l];
+                            const double a = reinterpret_cast<const double*>(R + 32)[l];
+                            const double vv = (key >> 16) == (uint32_t)P.SB ? 0.0
+                                                                            : v[vbase + (key & 0x7fffu)];
+                            sum += vv * a;
+                            if (key & kBandLast) {
+                                acc[key >> 16] += sum;
+                                sum = 0.0;
+                            }
+                        }
+                    }
+                }
+            }
+            const int nseg = std::min(P.SB, P.S - sb * P.SB);
+            for (int q = 0; q < nseg; q++) (*out)[(size_t)sb * P.SB + q] += acc[q];
+        }
+}
+
+int ipxgpu_band_selftest(int64_t m, int64_t n, const int64_t* AIp, const int64_t* AIi,
+                         const double* AIx, const double* x, int32_t force, double out[6]) {
+    if (m <= 0 || n <= 0 || !AIp || !AIi || !AIx || !x || !out)
+        return fail(IPXGPU_ERR_ARGUMENT, "invalid arguments");
+    const int64_t nnz = AIp[n];
+    if (nnz >= INT32_MAX || n >= INT32_MAX) return fail(IPXGPU_ERR_UNSUPPORTED, "too large");
+    try {
+        std::vector<int> cp((size_t)n + 1), ci((size_t)nnz);
+        for (int64_t j = 0; j <= n; j++) cp[j] = (int)AIp[j];
+        for (int64_t p = 0; p < nnz; p++) ci[p] = (int)AIi[p];
+        std::vector<int> rp((size_t)m + 1, 0), rj((size_t)nnz);
+        std::vector<double> rx((size_t)nnz);
+        for (int64_t p = 0; p < nnz; p++) rp[ci[p] + 1]++;
+        for (int64_t i = 0; i < m; i++) rp[i + 1] += rp[i];
+        {
+            std::vector<int> next(rp.begin(), rp.end() - 1);
+            for (int j = 0; j < (int)n; j++)
+                for (int p = cp[j]; p < cp[j + 1]; p++) {
+                    const int put = next[ci[p]]++;
+                    rj[put] = j;
+                    rx[put] = AIx[p];
+                }
+        }
+        std::vector<double> t_ref((size_t)n, 0.0), y_ref((size_t)m, 0.0);
+        for (int j = 0; j < (int)n; j++)
+            for (int p = cp[j]; p < cp[j + 1]; p++) t_ref[j] += x[ci[p]] * AIx[p];
+        for (int j = 0; j < (int)n; j++)
+            for (int p = cp[j]; p < cp[j + 1]; p++) y_ref[ci[p]] += t_ref[j] * AIx[p];
+        const double ratio = force ? 1e30 : 1.5;
+        for (int sweep = 0; sweep < 2; sweep++) {
+            double* o = out + 3 * sweep;
+            o[0] = o[1] = o[2] = 0.0;
+            BandPlan P;
+            const bool ok = sweep == 0 ? plan_band(&P, (int)m, (int)n, nnz, 148, ratio)
+                                       : plan_band(&P, (int)n, (int)m, nnz, 148, ratio);
+            if (!ok) continue;
+            BandHost H;
+            const bool built = sweep == 0 ? band_build(P, cp.data(), ci.data(), AIx, &H)
+                                          : band_build(P, rp.data(), rj.data(), rx.data(), &H);
+            if (!built) continue;
+            o[0] = 1.0;
+            std::vector<double> got;
+            band_emulate(P, H, sweep == 0 ? x : t_ref.data(), &got);
+            const std::vector<double>& ref = sweep == 0 ? t_ref : y_ref;
+            double e = 0.0;
+            for (size_t i = 0; i < ref.size(); i++) e = std::max(e, std::fabs(got[i] - ref[i]));
+            o[1] = e;
+            o[2] = H.rows > 0 ? (double)H.pad_entries / (32.0 * (double)H.rows) : 0.0;
+        }
+    } catch (const std::bad_alloc&) {
+        return fail(IPXGPU_ERR_OUT_OF_MEMORY, "host allocation failed");
+    }
+    return IPXGPU_OK;
+}
+
 // ---- measurement helper ----
 
 int ipxgpu_time_normal_apply(ipxgpu_ctx* c, int reps, int flush_l2, double out_ms[3]) {
