@@ -3,7 +3,7 @@
 //
 // Why: on B200 a divergent 8-byte global gather costs ~2 L1 wavefront cycles
 // per lane, which caps a sweep of A (normal_matrix.cc:67-75) near 20 % of HBM
-// bandwidth. A shared-memory gather costs ~0.2 cycles per lane. The gathered
+// bandwidth. A shared-memory gather costs a fraction of that. The gathered
 // vector does not fit in shared memory, so the matrix is re-tiled in two
 // dimensions at context creation:
 //
@@ -11,25 +11,27 @@
 //          into a ring of NBUF shared-memory buffers)
 //   blocks of the segment space      (SB accumulators in shared memory)
 //
-// An item = (segment block, run of consecutive bands) and is one CTA. Inside a
-// tile (block, band) every segment's entries form one run; runs are dealt to
-// the lanes of the CTA's consumer warps so that lane loads differ by at most
-// one entry, and a warp's share of the tile is stored as rows of 32 entries
-// (32 keys, 32 values: 384 contiguous bytes, fully coalesced). A warp's rows of
-// all the item's tiles are contiguous, so the warp streams them through a
-// register ring D rows deep without caring about tile boundaries; only the
-// consumption of the first row of a tile waits for the band's mbarrier.
-// A lane sums a run in a register and adds it to the segment's accumulator at
-// the run's last entry: no shuffles, no atomics, fixed summation order.
-//
-// One producer warp issues the bulk copies (cp.async.bulk, mbarrier
-// complete_tx); consumer warps release a buffer with an mbarrier arrive.
+// An item = (segment block, run of consecutive bands) and is one CTA: one
+// producer warp that issues the bulk copies (cp.async.bulk, mbarrier
+// complete_tx) and NW consumer warps. A segment belongs to ONE consumer warp
+// for the whole item (local segment % NW), so every addition to its
+// accumulator is issued by that warp in program order and the warps never
+// synchronise with each other: a warp waits only for the band it needs
+// (full mbarrier) and releases the one it has finished (empty mbarrier).
+// Inside a tile (block, band) a segment's entries form one run; a warp's runs
+// are dealt to its 32 lanes, longest first to the least loaded lane, and the
+// warp's share of the tile is stored as rows of 32 entries (32 keys, 32
+// values: 384 contiguous bytes, fully coalesced). The rows of all the item's
+// tiles are contiguous per warp, so the warp streams them through two
+// register batches of D rows (one in flight while the other is consumed)
+// without caring about tile boundaries. A lane sums a run in a register and
+// adds it to the segment's accumulator at the run's last entry: no shuffles,
+// no atomics, fixed summation order.
 #pragma once
 
 #include <stdint.h>
 
 #include <algorithm>
-#include <queue>
 #include <vector>
 
 #include "common.cuh"
@@ -62,7 +64,7 @@ struct BandDev {
     double* partials = nullptr;      // [nparts * S] when nparts > 1
     long long rows = 0;
     int debug = 0;
-    unsigned long long* trace = nullptr;  // tuning only: [nitems][NW + 4] globaltimer stamps
+    unsigned long long* trace = nullptr;  // tuning only: [nitems][2*NW + 4] globaltimer stamps
 };
 
 struct BandHost {
@@ -185,7 +187,7 @@ __device__ __forceinline__ double band_sweep_item(const BandDev& T, const BandAr
     double* v_buf = reinterpret_cast<double*>(smem_raw + 64 + rows_bytes);
     double* acc_s = v_buf + (size_t)NBUF * P.VB;
 
-    unsigned long long* trace = (DBG & 4) ? T.trace + (size_t)item * (NW + 4) : nullptr;
+    unsigned long long* trace = (DBG & 4) ? T.trace + (size_t)item * (2 * NW + 4) : nullptr;
     if ((DBG & 4) && tid == 0) trace[0] = globaltimer();
     const int sb = item / P.nparts;
     const int part = item - sb * P.nparts;
@@ -264,6 +266,7 @@ __device__ __forceinline__ double band_sweep_item(const BandDev& T, const BandAr
         const double* v_s = v_buf;
         double sum = 0.0;
         double last_v = 0.0;
+        unsigned long long waited = 0;  // DBG & 4: ns spent waiting for bands
         auto advance = [&](int rr) {
             do {
                 if (k >= 0) {
@@ -275,7 +278,10 @@ __device__ __forceinline__ double band_sweep_item(const BandDev& T, const BandAr
                 k++;
                 if (++buf == NBUF) buf = 0;
                 if (buf == 0) par ^= 1u;
+                unsigned long long tw0 = 0;
+                if (DBG & 4) tw0 = globaltimer();
                 if (!(DBG & 1)) mbar_wait(full + buf, par);
+                if (DBG & 4) waited += globaltimer() - tw0;
                 v_s = v_buf + (size_t)buf * P.VB;
                 boundary = rp[k + 1];
             } while (rr == boundary && k < nk - 1);
@@ -312,7 +318,10 @@ __device__ __forceinline__ double band_sweep_item(const BandDev& T, const BandAr
         // is in flight when the CTA exits) wait for the remaining bands
         while (k < nk - 1) advance(-1);
         if (DBG & 2) acc_s[lane] = sum;
-        if ((DBG & 4) && lane == 0) trace[4 + warp] = globaltimer();
+        if ((DBG & 4) && lane == 0) {
+            trace[4 + warp] = globaltimer();
+            trace[4 + NW + warp] = waited;
+        }
     }
     __syncthreads();
     if ((DBG & 4) && tid == 0) trace[2] = globaltimer();

@@ -348,7 +348,7 @@ static int run_cr_fused(ipxgpu_ctx* c, bool precond, bool zero_start, bool use_r
     F.trace = nullptr;
     F.trace_cap = 0;
     const bool tracing = trace_env != nullptr;
-    const int NWp = kBandWarps + 4;
+    const int NWp = 2 * kBandWarps + 4;
     if (item_trace) {
         IPXGPU_TRY(dev_alloc(&F.T1.trace, (size_t)F.T1.plan.nitems * NWp));
         IPXGPU_TRY(dev_alloc(&F.T2.trace, (size_t)F.T2.plan.nitems * NWp));

@@ -103,7 +103,7 @@ static KernelFn pick_reg(int dbg) {
 static KernelFn pick(const Cfg& c, int dbg) {
 #define REG(NW_, D_, LD_) \
     if (!c.tma && c.NW == NW_ && c.D == D_ && c.LD == LD_) return pick_reg<NW_, D_, LD_>(dbg);
-    REG(31, 4, 0) REG(31, 4, 1) REG(31, 4, 2) REG(31, 4, 3)
+    REG(31, 4, 0) REG(31, 3, 0) REG(31, 2, 0) REG(31, 4, 1) REG(31, 4, 2) REG(31, 4, 3)
     REG(16, 8, 0) REG(16, 8, 1) REG(24, 4, 0) REG(24, 4, 1)
     fprintf(stderr, "no instantiation tma=%d NW=%d D/NS=%d LD/C=%d\n", c.tma, c.NW, c.D, c.LD);
     exit(2);
@@ -411,7 +411,7 @@ int main(int argc, char** argv) {
         if (getenv("BSWEEP_TRACE")) {
             for (int sweep = 1; sweep <= 2; sweep++) {
                 BandDev& T = Ts[sweep];
-                const int NWp = c.NW + 4, ni = T.plan.nitems;
+                const int NWp = 2 * c.NW + 4, ni = T.plan.nitems;
                 CK(cudaMalloc(&T.trace, (size_t)ni * NWp * 8));
                 CK(cudaMemset(T.trace, 0, (size_t)ni * NWp * 8));
                 T.debug = 4;
@@ -454,6 +454,16 @@ int main(int argc, char** argv) {
                       "all warps done");
                 stats([&](int i) { return (double)(tr[(size_t)i * NWp + 3] - tr[(size_t)i * NWp + 2]); },
                       "epilogue");
+                stats([&](int i) {
+                    double sum = 0;
+                    for (int w = 0; w < c.NW; w++) sum += (double)tr[(size_t)i * NWp + 4 + c.NW + w];
+                    return sum / c.NW;
+                }, "band wait per warp (mean)");
+                stats([&](int i) {
+                    double mx = 0;
+                    for (int w = 0; w < c.NW; w++) mx = std::max(mx, (double)tr[(size_t)i * NWp + 4 + c.NW + w]);
+                    return mx;
+                }, "band wait per warp (max)");
                 stats([&](int i) { return (double)(tr[(size_t)i * NWp + 3] - t0); }, "item end (rel)");
                 T.debug = 0;
                 CK(cudaFree(T.trace));
