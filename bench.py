@@ -216,6 +216,12 @@ def run_gpu(args):
             uid.copy_(torch.frombuffer(bytearray(capi.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0)
         ctx.comm_init(bytes(uid.cpu().numpy().tobytes()))
+        if os.environ.get("IPXGPU_PEER", "1") != "0":
+            # NVLink peer exchange: the CR solve stays one persistent kernel per rank
+            mine = torch.frombuffer(bytearray(ctx.peer_export()), dtype=torch.uint8).to(dev)
+            allh = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+            dist.all_gather(allh, mine)
+            ctx.peer_import(b"".join(bytes(h.cpu().numpy().tobytes()) for h in allh))
     ctx.normal_prepare(W)
     ctx.diag_factorize(None, use_prepared=True)
     layout = ctx.layout()
@@ -305,7 +311,11 @@ def run_gpu(args):
             "config": {"workload": workload_name(world), "rows": m, "cols": n,
                        "nnz": int(lp.nnz), "cols_per_gpu": N_COLS,
                        "l2": "inputs larger than L2 (240 MB of matrix data per apply)",
-                       "collective": "none" if world == 1 else "ncclAllReduce(m+1 f64) per CR iteration"},
+                       "collective": "none" if world == 1 else (
+                           "in-kernel sum of the ranks' partial products over NVLink peer memory "
+                           "(P2P loads, per-slice flags) once per CR iteration"
+                           if os.environ.get("IPXGPU_PEER", "1") != "0"
+                           else "ncclAllReduce(m+1 f64) per CR iteration")},
             "e2e": {"value": e2e, "unit": "matvec/s",
                     "h2d_bytes_per_step": 16 * m, "d2h_bytes_per_step": 8 * m},
             "gpu_launches": int(launches),

@@ -40,7 +40,7 @@ EXPORTS = ("ipxgpu_default_options ipxgpu_last_error ipxgpu_device_count ipxgpu_
            "ipxgpu_normal_apply_dev ipxgpu_diag_factorize ipxgpu_diag_get ipxgpu_diag_set "
            "ipxgpu_diag_apply ipxgpu_pcr_solve ipxgpu_pcr_solve_dev ipxgpu_cr_solve ipxgpu_kktdiag_factorize "
            "ipxgpu_kktdiag_solve ipxgpu_lu_load ipxgpu_tri_solve ipxgpu_split_prepare "
-           "ipxgpu_split_apply ipxgpu_time_normal_apply ipxgpu_launch_count ipxgpu_band_selftest").split()
+           "ipxgpu_split_apply ipxgpu_time_normal_apply ipxgpu_launch_count ipxgpu_band_selftest ipxgpu_peer_export ipxgpu_peer_import").split()
 
 _lib = None
 
@@ -172,6 +172,16 @@ class Context:
 
     def comm_init(self, uid):
         _check(self.lib.ipxgpu_comm_init(self.h, C.c_char_p(uid)))
+
+    def peer_export(self):
+        """IPC handle (64 bytes) of this rank's exchange buffer."""
+        buf = C.create_string_buffer(64)
+        _check(self.lib.ipxgpu_peer_export(self.h, buf))
+        return buf.raw
+
+    def peer_import(self, handles):
+        """handles: the nranks 64-byte handles concatenated in rank order."""
+        _check(self.lib.ipxgpu_peer_import(self.h, C.c_char_p(bytes(handles))))
 
     # ---- NormalMatrix ----
     def normal_prepare(self, W):

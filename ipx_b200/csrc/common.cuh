@@ -49,7 +49,8 @@ struct HostMirror {
 struct CrState {
     double cdot, pdot, alpha, beta, resnorm, rsdot_prev, tol;
     long long iter, maxiter;
-    int done, errflag, precond, pad;
+    int done, errflag, precond;
+    int applies;  // C.Apply count of the solve (persistent kernel; peer-exchange generations)
     unsigned long long t_last;                      // globaltimer of last stamp
     unsigned long long t_op, t_pre, t_vec;          // accumulated ns
     unsigned long long t_B, t_Bt, t_NNt;

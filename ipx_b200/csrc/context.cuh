@@ -153,6 +153,14 @@ struct ipxgpu_ctx {
     ipxgpu::BandDev* band1 = nullptr;  // t = W .* (A'x): gather x, segments = columns
     ipxgpu::BandDev* band2 = nullptr;  // y = A t: gather t, segments = rows
 
+    // peer exchange (NVLink P2P) of the persistent CR kernel for sharded contexts
+    void* xchg = nullptr;             // own exchange buffer: y[2][xchg_mpad] doubles, then flags
+    size_t xchg_mpad = 0;
+    void* peer_base[16] = {nullptr};  // every rank's exchange buffer as mapped here (own: xchg)
+    double** peer_dev = nullptr;      // device copy of peer_base
+    bool peers_ready = false;
+    unsigned xchg_gen = 0;            // cross-GPU synchronisations performed so far
+
     // persistent CR kernel (pcr_fused.cuh): grid barrier words and per-CTA partials
     unsigned* fused_bar = nullptr;
     double* fused_red = nullptr;

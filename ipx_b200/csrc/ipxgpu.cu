@@ -275,7 +275,7 @@ static inline void cpu_relax() {
 // ---- persistent CR kernel (pcr_fused.cuh) ----
 
 static bool fused_available(ipxgpu_ctx* c) {
-    if (c->nranks != 1 || !c->band1 || !c->band2 || c->m <= 0) return false;
+    if ((c->nranks != 1 && !c->peers_ready) || !c->band1 || !c->band2 || c->m <= 0) return false;
     if (const char* env = std::getenv("IPXGPU_FUSED"))
         if (std::atoi(env) == 0) return false;
     return true;
@@ -338,7 +338,12 @@ static int run_cr_fused(ipxgpu_ctx* c, bool precond, bool zero_start, bool use_r
     F.v.resscale = use_resscale ? c->v_resscale : nullptr;
     F.rhs = c->v_rhs;
     F.Wc = c->Wc;
-    F.Ws = c->Ws;
+    F.Ws = (c->rank == 0) ? c->Ws : nullptr;  // the slack term is added on one rank
+    F.nranks = c->nranks;
+    F.rank = c->rank;
+    F.peers = c->peer_dev;
+    F.xmpad = c->xchg_mpad;
+    F.xgen_base = c->xchg_gen;
     F.t = c->t;
     F.zero_start = zero_start ? 1 : 0;
     F.sync = GridSync{c->fused_bar, c->fused_red};
@@ -377,6 +382,13 @@ static int run_cr_fused(ipxgpu_ctx* c, bool precond, bool zero_start, bool use_r
     }
     IPXGPU_CUDA(cudaStreamSynchronize(c->stream));
     IPXGPU_CUDA(cudaMemcpy(&h, c->st_dev, sizeof h, cudaMemcpyDeviceToHost));
+    if (c->nranks > 1) {
+        c->xchg_gen += (unsigned)h.applies;
+        double aborted = 0.0;
+        IPXGPU_CUDA(cudaMemcpy(&aborted, F.abort_word, sizeof(double), cudaMemcpyDeviceToHost));
+        if (aborted == 2.0)
+            return fail(IPXGPU_ERR_NCCL, "peer exchange timed out: a rank did not reach the CR solve");
+    }
     if (tracing) {
         // CTA 0, 10 stamps per iteration after the initialisation:
         // dir | dir sync | upd | upd sync | s1 | s1 sync | s2 | s2 sync | comb | comb sync
@@ -601,6 +613,10 @@ void ipxgpu_destroy(ipxgpu_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     destroy_split(c);
+    for (int r = 0; r < c->nranks && r < 16; r++)
+        if (r != c->rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
+    if (c->xchg) cudaFree(c->xchg);
+    dev_free(c->peer_dev);
     dev_free(c->fused_bar);
     dev_free(c->fused_red);
     if (c->band1) { free_band(c->band1); delete c->band1; }
@@ -885,6 +901,45 @@ int ipxgpu_comm_unique_id(char id[128]) {
     ncclResult_t r = api->GetUniqueId(&uid);
     if (r != ncclSuccess) return fail(IPXGPU_ERR_NCCL, "ncclGetUniqueId failed");
     std::memcpy(id, &uid, 128);
+    return IPXGPU_OK;
+}
+
+int ipxgpu_peer_export(ipxgpu_ctx* c, char handle[64]) {
+    IPXGPU_TRY(check_ctx(c));
+    if (!handle) return fail(IPXGPU_ERR_ARGUMENT, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
+    if (c->nranks < 2 || c->nranks > 16) return fail(IPXGPU_ERR_STATE, "peer exchange needs 2..16 ranks");
+    if (!c->xchg) {
+        c->xchg_mpad = ((size_t)c->m + 31) & ~(size_t)31;
+        const size_t bytes = 2 * c->xchg_mpad * sizeof(double) +
+                             (size_t)c->nranks * c->num_sms * sizeof(unsigned);
+        IPXGPU_CUDA(cudaMalloc(&c->xchg, bytes));  // plain cudaMalloc: IPC-exportable
+        IPXGPU_CUDA(cudaMemset(c->xchg, 0, bytes));
+        c->xchg_gen = 0;
+    }
+    cudaIpcMemHandle_t h;
+    IPXGPU_CUDA(cudaIpcGetMemHandle(&h, c->xchg));
+    std::memcpy(handle, &h, 64);
+    return IPXGPU_OK;
+}
+
+int ipxgpu_peer_import(ipxgpu_ctx* c, const char* handles) {
+    IPXGPU_TRY(check_ctx(c));
+    if (!handles) return fail(IPXGPU_ERR_ARGUMENT, "null argument");
+    if (!c->xchg) return fail(IPXGPU_ERR_STATE, "call ipxgpu_peer_export first");
+    for (int r = 0; r < c->nranks; r++) {
+        if (r == c->rank) {
+            c->peer_base[r] = c->xchg;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handles + (size_t)r * 64, 64);
+        IPXGPU_CUDA(cudaIpcOpenMemHandle(&c->peer_base[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    IPXGPU_TRY(dev_alloc(&c->peer_dev, (size_t)c->nranks));
+    IPXGPU_CUDA(cudaMemcpy(c->peer_dev, c->peer_base, sizeof(void*) * c->nranks,
+                           cudaMemcpyHostToDevice));
+    c->peers_ready = true;
     return IPXGPU_OK;
 }
 

@@ -53,6 +53,12 @@ struct FusedArgs {
     const volatile int* abort_flag;  // host-mapped; nonzero asks the solve to stop
     unsigned long long* trace;       // tuning only: globaltimer of CTA 0 at every stage end
     int trace_cap;
+    // Sharded contexts: every rank's exchange buffer (as mapped in this process),
+    // y[2][xmpad] doubles followed by flags[nranks][gridDim.x]. nranks == 1: unused.
+    int nranks, rank;
+    double* const* peers;
+    size_t xmpad;
+    unsigned xgen_base;              // cross-GPU synchronisations before this solve
 };
 
 constexpr int kFusedStages = 6;
@@ -181,6 +187,7 @@ pcr_fused_kernel(FusedArgs F) {
         if (lead && F.trace && ntrace < F.trace_cap) F.trace[ntrace++] = globaltimer();
     };
     unsigned gen = 0;  // barriers passed so far (identical in all CTAs)
+    int s_applies = 0; // C.Apply calls so far (identical in all CTAs and ranks)
     double r0 = 0.0, r1 = 0.0, r2 = 0.0;
     // Barrier with reduction; (a, b, c) are this thread's shares of sum, sum,
     // max. Totals land in r0, r1, r2 of every thread.
@@ -208,14 +215,71 @@ pcr_fused_kernel(FusedArgs F) {
         sync_plain();
         const int nparts = F.T2.plan.nparts;
         double dot = 0.0;
-        for (int i = i0 + tid; i < i1; i += nthr) {
-            double acc = 0.0;
+        if (F.nranks == 1) {
+            for (int i = i0 + tid; i < i1; i += nthr) {
+                double acc = 0.0;
 #pragma unroll 8
-            for (int p = 0; p < nparts; p++) acc += __ldcg(F.T2.partials + (size_t)p * m + i);
-            const double xv = x[i];
-            const double yv = (F.Ws ? __dmul_rn(xv, F.Ws[i]) : 0.0) + acc;
-            lhs[i] = yv;
-            dot += __dmul_rn(xv, yv);
+                for (int p = 0; p < nparts; p++) acc += __ldcg(F.T2.partials + (size_t)p * m + i);
+                const double xv = x[i];
+                const double yv = (F.Ws ? __dmul_rn(xv, F.Ws[i]) : 0.0) + acc;
+                lhs[i] = yv;
+                dot += __dmul_rn(xv, yv);
+            }
+        } else {
+            // Column shards: this rank's partial product of the slice goes to its
+            // exchange buffer; the same CTA of every rank then sums the ranks'
+            // partials of the slice in rank order (bit-identical on all ranks)
+            // with P2P loads. Synchronisation is per slice: a flag per (rank, CTA)
+            // in every peer's buffer, no collective and no extra grid barrier.
+            const unsigned gen = F.xgen_base + (unsigned)(++s_applies);
+            const size_t off = (size_t)(gen & 1u) * F.xmpad;
+            double* mine = F.peers[F.rank] + off;
+            for (int i = i0 + tid; i < i1; i += nthr) {
+                double acc = 0.0;
+#pragma unroll 8
+                for (int p = 0; p < nparts; p++) acc += __ldcg(F.T2.partials + (size_t)p * m + i);
+                mine[i] = (F.Ws ? __dmul_rn(x[i], F.Ws[i]) : 0.0) + acc;
+            }
+            __syncthreads();
+            const size_t flag_off = 2 * F.xmpad;  // in doubles
+            if (tid == 0) __threadfence_system();
+            __syncthreads();
+            if (tid < F.nranks) {
+                // signal rank `tid` that slice blockIdx.x of this rank is ready ...
+                unsigned* remote = reinterpret_cast<unsigned*>(F.peers[tid] + flag_off) +
+                                   (size_t)F.rank * gridDim.x + blockIdx.x;
+                asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(gen) : "memory");
+                // ... and wait for rank `tid`'s slice
+                const unsigned* local = reinterpret_cast<const unsigned*>(F.peers[F.rank] + flag_off) +
+                                        (size_t)tid * gridDim.x + blockIdx.x;
+                unsigned now;
+                long long spins = 0;
+                do {
+                    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(now) : "l"(local) : "memory");
+                    if ((++spins & 0xffff) == 0) {
+                        // a peer that never arrives must not hang this GPU
+                        if (spins > (1ll << 24) || __ldcg(F.abort_word) != 0.0) {
+                            *F.abort_word = 2.0;
+                            break;
+                        }
+                    }
+                } while ((int)(now - gen) < 0);
+                __threadfence_system();
+            }
+            __syncthreads();
+            for (int i = i0 + tid; i < i1; i += nthr) {
+                double yv = 0.0;
+                for (int r = 0; r < F.nranks; r++) {
+                    double part;
+                    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];"
+                                 : "=d"(part)
+                                 : "l"(F.peers[r] + off + i)
+                                 : "memory");
+                    yv += part;
+                }
+                lhs[i] = yv;
+                dot += __dmul_rn(x[i], yv);
+            }
         }
         sync_stage(kStCombine, dot, 0.0, 0.0);
         stamp_lead(kSlotOp);
@@ -361,6 +425,7 @@ pcr_fused_kernel(FusedArgs F) {
     }
 
     if (lead) {
+        s_st.applies = s_applies;
         *F.st = s_st;
         publish(F.st);
     }
