@@ -18,11 +18,13 @@ from ipx_b200 import capi, lpgen  # noqa: E402
 rank = int(os.environ.get("RANK", "0"))
 world = int(os.environ.get("WORLD_SIZE", "1"))
 local = int(os.environ.get("LOCAL_RANK", "0"))
+if rank != 0:
+    os.environ.pop("IPXGPU_FUSED_TRACE", None)  # tuning trace: rank 0 only
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 
-m, ncols = 20000, 400000
+m, ncols = (100000, 1000000) if os.environ.get("CHECK_SHARDED_BIG") else (20000, 400000)
 lp = lpgen.random_sparse_lp(m, ncols * world, 10, 77)
 n = lp.n
 AIp, AIi, AIx = lp.solver_form()
