@@ -197,49 +197,66 @@ __device__ __forceinline__ double band_sweep_item(const BandDev& T, const BandAr
     const int nk = min(P.NVB, vb0 + P.K) - vb0;
     const int rot = sb % nk;
 
-    if (tid == 0) {
+    // Stages band k of the item into ring buffer b (producer lane only).
+    auto stage_band = [&](int k, int b, uint64_t keep) {
+        int r = k + rot;
+        if (r >= nk) r -= nk;
+        const int vbase = (vb0 + r) * P.VB;
+        const int vlen = min(P.VB, P.V - vbase);
+        double* dst = v_buf + (size_t)b * P.VB;
+        const unsigned bytes = (unsigned)(vlen & ~1) * 8u;
+        if (vlen & 1) dst[vlen - 1] = A.v[vbase + vlen - 1];
+        mbar_arrive_expect_tx(full + b, bytes);
+        // at most 16 KB per copy keeps several copies in flight
+        for (unsigned off = 0; off < bytes; off += 16384u) {
+            const unsigned n = min(16384u, bytes - off);
+            bulk_g2s(reinterpret_cast<unsigned char*>(dst) + off,
+                     reinterpret_cast<const unsigned char*>(A.v + vbase) + off, n, full + b, keep);
+        }
+    };
+    const bool producer = tid == NW * 32;
+    uint64_t keep = 0;
+    if (producer) {
+        // The producer lane sets up the barriers and starts the first NBUF bands
+        // at once, while the other threads clear the accumulators and fetch the
+        // row table: the first band is (nearly) there when the consumers start.
         for (int b = 0; b < NBUF; b++) {
             mbar_init(full + b, 1);
             mbar_init(empty + b, NW);
         }
         mbar_fence_init();
-    }
-    for (int s = tid; s <= nseg; s += (NW + 1) * 32) acc_s[s] = 0.0;
-    {
+        keep = policy_evict_last();
+        if (!(DBG & 1))
+            for (int k = 0; k < NBUF && k < nk; k++) stage_band(k, k, keep);
+    } else {
+        const int ptid = tid < NW * 32 ? tid : tid - 1;  // the other 32*(NW+1) - 1 threads
+        const int pcount = (NW + 1) * 32 - 1;
+        for (int s = ptid; s <= nseg; s += pcount) acc_s[s] = 0.0;
         const int* src = T.row_ptr + (size_t)item * NW * (P.K + 1);
-        for (int i = tid; i < NW * (P.K + 1); i += (NW + 1) * 32) s_rows[i] = src[i];
+        for (int i = ptid; i < NW * (P.K + 1); i += pcount) s_rows[i] = src[i];
     }
     __syncthreads();
     if ((DBG & 4) && tid == 0) trace[1] = globaltimer();
 
     if (warp == NW) {
-        // ===== producer: stage the item's bands =====
+        // ===== producer: stage the remaining bands as buffers are released =====
         if (lane == 0 && !(DBG & 1)) {
             int b = 0;
-            unsigned par = 1;  // parity of the previous use of buffer b
-            const uint64_t keep = policy_evict_last();
-            for (int k = 0; k < nk; k++) {
-                if (k >= NBUF) mbar_wait(empty + b, par);
-                int r = k + rot;
-                if (r >= nk) r -= nk;
-                const int vbase = (vb0 + r) * P.VB;
-                const int vlen = min(P.VB, P.V - vbase);
-                double* dst = v_buf + (size_t)b * P.VB;
-                const unsigned bytes = (unsigned)(vlen & ~1) * 8u;
-                if (vlen & 1) dst[vlen - 1] = A.v[vbase + vlen - 1];
-                mbar_arrive_expect_tx(full + b, bytes);
-                // at most 16 KB per copy keeps several copies in flight
-                for (unsigned off = 0; off < bytes; off += 16384u) {
-                    const unsigned n = min(16384u, bytes - off);
-                    bulk_g2s(reinterpret_cast<unsigned char*>(dst) + off,
-                             reinterpret_cast<const unsigned char*>(A.v + vbase) + off, n,
-                             full + b, keep);
-                }
+            unsigned par = 0;  // parity of the previous use of buffer b
+            for (int k = NBUF; k < nk; k++) {
+                mbar_wait(empty + b, par);
+                stage_band(k, b, keep);
                 if (++b == NBUF) {
                     b = 0;
                     par ^= 1u;
                 }
             }
+        } else if (lane > 0 && mode == kBandColScale && A.W != nullptr) {
+            // idle lanes: pull the weights of the epilogue into L2 meanwhile
+            const char* wbase = reinterpret_cast<const char*>(A.W + seg_base);
+            const long long wbytes = (long long)nseg * 8;
+            for (long long o = (long long)(lane - 1) * 128; o < wbytes; o += 31 * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(wbase + o));
         }
     } else {
         // ===== consumers =====
