@@ -299,6 +299,7 @@ static int run_cr_fused(ipxgpu_ctx* c, bool precond, bool zero_start, bool use_r
         if (per_sm < 1) return fail(IPXGPU_ERR_STATE, "persistent CR kernel does not fit an SM");
         c->fused_grid = c->num_sms;  // one CTA per SM (shared memory bound)
         IPXGPU_TRY(dev_alloc(&c->fused_bar, 1));
+        IPXGPU_TRY(dev_alloc(&c->fused_tickets, (size_t)c->band2->plan.NSB));
         IPXGPU_TRY(dev_alloc(&c->fused_red, (size_t)kFusedStages * 3 * c->fused_grid + 1));
     }
     if (!c->band2->partials)
@@ -321,6 +322,8 @@ static int run_cr_fused(ipxgpu_ctx* c, bool precond, bool zero_start, bool use_r
     IPXGPU_CUDA(cudaMemsetAsync(c->fused_red + (size_t)kFusedStages * 3 * c->fused_grid, 0,
                                 sizeof(double), c->stream));
     IPXGPU_CUDA(cudaMemsetAsync(c->fused_bar, 0, sizeof(unsigned), c->stream));
+    IPXGPU_CUDA(cudaMemsetAsync(c->fused_tickets, 0, sizeof(unsigned) * c->band2->plan.NSB,
+                                c->stream));
     if (zero_start) IPXGPU_CUDA(cudaMemsetAsync(c->v_y, 0, sizeof(double) * m, c->stream));
 
     FusedArgs F;
@@ -348,6 +351,7 @@ static int run_cr_fused(ipxgpu_ctx* c, bool precond, bool zero_start, bool use_r
     F.zero_start = zero_start ? 1 : 0;
     F.sync = GridSync{c->fused_bar, c->fused_red};
     F.abort_word = c->fused_red + (size_t)kFusedStages * 3 * c->fused_grid;
+    F.block_tickets = c->fused_tickets;
     F.st = c->st_dev;
     F.abort_flag = &c->mirror_dev->abort;
     F.trace = nullptr;
@@ -618,6 +622,7 @@ void ipxgpu_destroy(ipxgpu_ctx* c) {
     if (c->xchg) cudaFree(c->xchg);
     dev_free(c->peer_dev);
     dev_free(c->fused_bar);
+    dev_free(c->fused_tickets);
     dev_free(c->fused_red);
     if (c->band1) { free_band(c->band1); delete c->band1; }
     if (c->band2) { free_band(c->band2); delete c->band2; }
@@ -721,6 +726,15 @@ int ipxgpu_create(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp, co
     c->csc.nnz = nnz;
 
     cudaStream_t s = c->stream;
+    const bool timing = std::getenv("IPXGPU_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ipxgpu_create] %-28s %8.1f ms\n", what,
+                1e3 * std::chrono::duration<double>(now - t_last).count());
+        t_last = now;
+    };
     try {
         // Shard CSC with int32 indices.
         std::vector<int> cp(nloc + 1), ci((size_t)nnz);
@@ -737,6 +751,7 @@ int ipxgpu_create(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp, co
             IPXGPU_CUDA(cudaMemcpyAsync(c->csc.val, AIx + base, sizeof(double) * nnz,
                                         cudaMemcpyHostToDevice, s));
 
+        lap("CSC int32 + upload");
         // Panels: t-slice of at most panel_cols columns (default 2M = 16 MB).
         int64_t pc = opt.panel_cols > 0 ? opt.panel_cols : (int64_t)2 << 20;
         const char* env_pc = std::getenv("IPXGPU_PANEL_COLS");
@@ -779,6 +794,7 @@ int ipxgpu_create(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp, co
             max_grid = std::max(max_grid, std::max(P.col_tiles.ntiles, P.row_tiles.ntiles));
             IPXGPU_CUDA(cudaStreamSynchronize(s));  // host vectors die here
         }
+        lap("panels: CSR, tiles, upload");
         // Banded shared-memory sweeps (band_sweep.cuh) carry the normal-matrix
         // apply wherever the structure suits them. IPXGPU_SWEEP=generic turns
         // them off, IPXGPU_SWEEP=band forces them whenever a plan fits.
@@ -795,6 +811,7 @@ int ipxgpu_create(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp, co
                     c->band1->plan = plan;
                     const int rc1 = build_band(c, c->band1, cp.data(), ci.data(), AIx + base,
                                                max_pad);
+                    lap("band layout sweep 1");
                     if (rc1 == IPXGPU_ERR_UNSUPPORTED) {  // structure suits the generic sweep
                         free_band(c->band1);
                         delete c->band1;
@@ -817,10 +834,12 @@ int ipxgpu_create(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp, co
                             rj[put] = j;
                             rx[put] = AIx[base + p];
                         }
+                    lap("CSR for sweep 2");
                     c->band2 = new BandDev();
                     c->band2->plan = plan;
                     const int rc2 = build_band(c, c->band2, rp.data(), rj.data(), rx.data(),
                                                max_pad);
+                    lap("band layout sweep 2");
                     if (rc2 == IPXGPU_ERR_UNSUPPORTED) {
                         free_band(c->band2);
                         delete c->band2;
@@ -845,6 +864,7 @@ int ipxgpu_create(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp, co
         std::memset(c->mirror_host, 0, sizeof(HostMirror));
         IPXGPU_CUDA(cudaHostGetDevicePointer((void**)&c->mirror_dev, c->mirror_host, 0));
         IPXGPU_CUDA(cudaStreamSynchronize(s));
+        lap("work vectors");
     } catch (const std::bad_alloc&) {
         return fail(IPXGPU_ERR_OUT_OF_MEMORY, "host allocation failed while building layouts");
     }

@@ -49,6 +49,7 @@ struct FusedArgs {
     int zero_start;
     GridSync sync;
     double* abort_word; // set nonzero by CTA 0 when the host asked to stop
+    unsigned* block_tickets;  // [T2.plan.NSB], zero before the launch: items done per row block
     CrState* st;
     const volatile int* abort_flag;  // host-mapped; nonzero asks the solve to stop
     unsigned long long* trace;       // tuning only: globaltimer of CTA 0 at every stage end
@@ -210,12 +211,50 @@ pcr_fused_kernel(FusedArgs F) {
             band_sweep_item<NW, D, DBG>(F.T1, a1, kBandColScale, item, smem_raw);
         sync_plain();
         BandArgs a2{F.t, nullptr, nullptr, nullptr, nullptr, kApplyPlain, kSlotNone};
-        for (int item = blockIdx.x; item < F.T2.plan.nitems; item += gridDim.x)
-            band_sweep_item<NW, D, DBG>(F.T2, a2, kBandPartial, item, smem_raw);
-        sync_plain();
         const int nparts = F.T2.plan.nparts;
         double dot = 0.0;
-        if (F.nranks == 1) {
+        if (F.nranks == 1 && F.T2.plan.nitems <= (int)gridDim.x) {
+            // The nparts items of a row block (all resident: one item per CTA)
+            // meet at the block's counter when their partials are written; each
+            // then combines its share of the block's rows, in part order. No
+            // separate combine stage, one grid barrier less.
+            ++s_applies;
+            if ((int)blockIdx.x < F.T2.plan.nitems) {
+                const int item = blockIdx.x;
+                band_sweep_item<NW, D, DBG>(F.T2, a2, kBandPartial, item, smem_raw);
+                const int sb = item / nparts, part = item - sb * nparts;
+                if (tid == 0) {
+                    __threadfence();
+                    unsigned* cnt = F.block_tickets + sb;
+                    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(cnt) : "memory");
+                    const unsigned target = (unsigned)s_applies * (unsigned)nparts;
+                    unsigned now;
+                    do {
+                        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(cnt) : "memory");
+                    } while ((int)(now - target) < 0);
+                    __threadfence();
+                }
+                __syncthreads();
+                const int rb = sb * F.T2.plan.SB, re = min(m, rb + F.T2.plan.SB);
+                const int share = (re - rb + nparts - 1) / nparts;
+                const int q0 = rb + part * share, q1 = min(re, q0 + share);
+                for (int i = q0 + tid; i < q1; i += nthr) {
+                    double acc = 0.0;
+#pragma unroll 8
+                    for (int p = 0; p < nparts; p++) acc += __ldcg(F.T2.partials + (size_t)p * m + i);
+                    const double xv = __ldcg(x + i);
+                    const double yv = (F.Ws ? __dmul_rn(xv, F.Ws[i]) : 0.0) + acc;
+                    lhs[i] = yv;
+                    dot += __dmul_rn(xv, yv);
+                }
+            }
+        } else {
+            ++s_applies;
+            for (int item = blockIdx.x; item < F.T2.plan.nitems; item += gridDim.x)
+                band_sweep_item<NW, D, DBG>(F.T2, a2, kBandPartial, item, smem_raw);
+            sync_plain();
+        }
+        if (F.nranks == 1 && F.T2.plan.nitems > (int)gridDim.x) {
             for (int i = i0 + tid; i < i1; i += nthr) {
                 double acc = 0.0;
 #pragma unroll 8
@@ -225,13 +264,13 @@ pcr_fused_kernel(FusedArgs F) {
                 lhs[i] = yv;
                 dot += __dmul_rn(xv, yv);
             }
-        } else {
+        } else if (F.nranks > 1) {
             // Column shards: this rank's partial product of the slice goes to its
             // exchange buffer; the same CTA of every rank then sums the ranks'
             // partials of the slice in rank order (bit-identical on all ranks)
             // with P2P loads. Synchronisation is per slice: a flag per (rank, CTA)
             // in every peer's buffer, no collective and no extra grid barrier.
-            const unsigned gen = F.xgen_base + (unsigned)(++s_applies);
+            const unsigned gen = F.xgen_base + (unsigned)s_applies;
             const size_t off = (size_t)(gen & 1u) * F.xmpad;
             double* mine = F.peers[F.rank] + off;
             for (int i = i0 + tid; i < i1; i += nthr) {
@@ -293,7 +332,7 @@ pcr_fused_kernel(FusedArgs F) {
     {
         double rs = 0.0, mx = 0.0;
         for (int i = i0 + tid; i < i1; i += nthr) {
-            const double ri = F.zero_start ? F.rhs[i] : F.rhs[i] - v.Cs[i];
+            const double ri = F.zero_start ? F.rhs[i] : F.rhs[i] - __ldcg(v.Cs + i);
             v.r[i] = ri;
             v.p[i] = 0.0;
             v.Cp[i] = 0.0;
@@ -332,7 +371,7 @@ pcr_fused_kernel(FusedArgs F) {
         double pd = 0.0, rs = 0.0;
         for (int i = i0 + tid; i < i1; i += nthr) {
             const double pn = sv[i] + __dmul_rn(beta, v.p[i]);
-            const double cpn = v.Cs[i] + __dmul_rn(beta, v.Cp[i]);
+            const double cpn = __ldcg(v.Cs + i) + __dmul_rn(beta, v.Cp[i]);
             v.p[i] = pn;
             v.Cp[i] = cpn;
             if (precond) {

@@ -22,7 +22,10 @@ args = ap.parse_args()
 lp = lpgen.transportation_lp(2000, 5000, 1004) if args.transport else \
     lpgen.random_sparse_lp(args.rows, args.cols, args.k, 1002)
 m, n = lp.m, lp.n
+import time
+_t0 = time.time()
 ctx = capi.Context(m, n, *lp.solver_form())
+print(f"context creation {time.time() - _t0:.2f} s")
 W = lpgen.weights(n + m, "mid", 1003)
 ctx.normal_prepare(W)
 ctx.diag_factorize(None, use_prepared=True)
