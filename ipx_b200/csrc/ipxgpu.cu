@@ -276,6 +276,7 @@ static inline void cpu_relax() {
 
 static bool fused_available(ipxgpu_ctx* c) {
     if ((c->nranks != 1 && !c->peers_ready) || !c->band1 || !c->band2 || c->m <= 0) return false;
+    if (c->band1->plan.nparts != 1) return false;  // sweep 1 must write t directly
     if (const char* env = std::getenv("IPXGPU_FUSED"))
         if (std::atoi(env) == 0) return false;
     return true;
