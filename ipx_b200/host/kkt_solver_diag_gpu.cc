@@ -15,7 +15,10 @@
 #include "kkt_solver_diag.h"
 
 #include <cassert>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 
 #include "conjugate_residuals.h"
@@ -42,12 +45,22 @@ KKTSolverDiag::KKTSolverDiag(const Control& control, const Model& model)
 void KKTSolverDiag::_Factorize(Iterate* pt, Info* info) {
     const Int m = model_.rows();
     const Int n = model_.cols();
+    static const bool timing = std::getenv("IPXGPU_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[KKTSolverDiag::_Factorize] %-24s %8.2f ms\n", what,
+                     1e3 * std::chrono::duration<double>(now - t_last).count());
+        t_last = now;
+    };
     iter_ = 0;
     factorized_ = false;
     const bool host_precond = control_.precond_dense_cols() && model_.num_dense_cols() > 0;
 
     if (!host_precond) {
         const ipxb200::ContextRef ref = ipxb200::ContextFor(model_);
+        lap("ContextFor");
         if (pt) {
             Check(ipxgpu_kktdiag_factorize(ref.ctx, &pt->xl()[0], &pt->xu()[0], &pt->zl()[0],
                                            &pt->zu()[0], pt->mu(), &W_[0],
@@ -59,6 +72,7 @@ void KKTSolverDiag::_Factorize(Iterate* pt, Info* info) {
         // Weights and diagonal are already resident: the member operators only
         // register themselves (and fetch the diagonal).
         ipxb200::SetResidentHint(ref.ctx, &W_[0]);
+        lap("ipxgpu_kktdiag_factorize");
     } else {
         // Host weight build, reference src/kkt_solver_diag.cc:24-56.
         if (pt) {
@@ -77,7 +91,9 @@ void KKTSolverDiag::_Factorize(Iterate* pt, Info* info) {
         for (Int i = 0; i < m; i++) resscale_[i] = 1.0 / std::sqrt(W_[n + i]);
     }
     normal_matrix_.Prepare(&W_[0]);
+    lap("NormalMatrix::Prepare");
     precond_.Factorize(&W_[0], control_.precond_dense_cols(), info);
+    lap("DiagonalPrecond::Factorize");
     if (info->errflag) return;
     factorized_ = true;
 }

@@ -35,6 +35,8 @@ def _case(kind):
         return lpgen.transportation_lp(20, 3000, 23)
     if kind == "ragged":
         return _ragged_lp()
+    if kind == "tall":  # more rows than the planner gives one block: sweep 1 in several parts
+        return lpgen.random_sparse_lp(60000, 30000, 10, 24)
     raise ValueError(kind)
 
 
@@ -246,7 +248,7 @@ def test_launch_counter_moves(problem):
     assert ctx.launch_count() > before
 
 
-@pytest.mark.parametrize("kind", ["random_mid", "transport", "ragged"])
+@pytest.mark.parametrize("kind", ["random_mid", "transport", "ragged", "tall"])
 def test_band_sweeps_forced(capi, oracle, kind, monkeypatch):
     """The banded shared-memory sweeps, forced on small shapes (IPXGPU_SWEEP=band), give the
     same operator as the oracle."""
