@@ -134,7 +134,7 @@ struct ipxgpu_ctx {
            *v_Cs = nullptr, *v_q = nullptr, *v_rhs = nullptr, *v_resscale = nullptr,
            *v_hist = nullptr;
     int64_t hist_cap = 0;
-    double* nvec[3] = {nullptr, nullptr, nullptr};  // n+m scratch (kktdiag path)
+    double* nvec[4] = {nullptr, nullptr, nullptr, nullptr};  // n+m scratch (kktdiag path)
 
     ipxgpu::Reduce red{nullptr, nullptr};
     int red_cap = 0;

@@ -259,7 +259,7 @@ static int ensure_cr_buffers(ipxgpu_ctx* c, int64_t hist_cap) {
 }
 
 static int ensure_nvecs(ipxgpu_ctx* c) {
-    for (int k = 0; k < 3; k++)
+    for (int k = 0; k < 4; k++)
         if (!c->nvec[k]) IPXGPU_TRY(dev_alloc(&c->nvec[k], (size_t)(c->n + c->m)));
     return IPXGPU_OK;
 }
@@ -643,7 +643,7 @@ void ipxgpu_destroy(ipxgpu_ctx* c) {
     dev_free(c->v_y); dev_free(c->v_r); dev_free(c->v_s); dev_free(c->v_p); dev_free(c->v_Cp);
     dev_free(c->v_Cs); dev_free(c->v_q); dev_free(c->v_rhs); dev_free(c->v_resscale);
     dev_free(c->v_hist);
-    for (int k = 0; k < 3; k++) dev_free(c->nvec[k]);
+    for (int k = 0; k < 4; k++) dev_free(c->nvec[k]);
     dev_free(c->red.partials);
     dev_free(c->red.ticket);
     dev_free(c->st_dev);
@@ -670,6 +670,7 @@ int ipxgpu_create(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp, co
     if (opt.nranks < 1 || opt.rank < 0 || opt.rank >= opt.nranks)
         return fail(IPXGPU_ERR_ARGUMENT, "invalid rank/nranks");
 
+    const auto t_enter = std::chrono::steady_clock::now();
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -728,7 +729,11 @@ int ipxgpu_create(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp, co
 
     cudaStream_t s = c->stream;
     const bool timing = std::getenv("IPXGPU_TIMING") != nullptr;
+    IPXGPU_CUDA(cudaFree(nullptr));  // forces the device context into existence here
     auto t_last = std::chrono::steady_clock::now();
+    if (timing)
+        fprintf(stderr, "[ipxgpu_create] %-28s %8.1f ms\n", "CUDA runtime / context",
+                1e3 * std::chrono::duration<double>(t_last - t_enter).count());
     auto lap = [&](const char* what) {
         if (!timing) return;
         const auto now = std::chrono::steady_clock::now();
@@ -1206,31 +1211,25 @@ int ipxgpu_kktdiag_factorize(ipxgpu_ctx* c, const double* xl, const double* xu, 
     if (xl) {
         if (!xu || !zl || !zu) return fail(IPXGPU_ERR_ARGUMENT, "incomplete iterate");
         IPXGPU_TRY(ensure_nvecs(c));
-        // xl, xu, zl stream through the scratch vectors; zu through W_full's
-        // future tenant is not possible, so stage zu in the CR rhs-sized area
-        // only when it fits; otherwise reuse nvec[0] after consumption.
+        // The four iterate vectors stream through persistent scratch vectors (no
+        // allocation per call: cudaMalloc/cudaFree cost up to hundreds of ms).
         double* d_xl = c->nvec[0];
         double* d_xu = c->nvec[1];
         double* d_zl = c->nvec[2];
-        double* d_zu = nullptr;
-        IPXGPU_TRY(dev_alloc(&d_zu, (size_t)nm));
+        double* d_zu = c->nvec[3];
         cudaStream_t s = c->stream;
         auto up = [&](double* d, const double* h) {
             return cudaMemcpyAsync(d, h, sizeof(double) * nm, cudaMemcpyHostToDevice, s);
         };
         cudaError_t e1 = up(d_xl, xl), e2 = up(d_xu, xu), e3 = up(d_zl, zl), e4 = up(d_zu, zu);
-        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) {
-            cudaFree(d_zu);
+        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess)
             return fail(IPXGPU_ERR_CUDA, "iterate upload failed");
-        }
         kkt_weights_kernel<<<grid, kBlock, 0, s>>>(nm, d_xl, d_xu, d_zl, d_zu, c->W_full, c->red,
                                                    c->scalars);
         kkt_weights_fix_kernel<<<grid, kBlock, 0, s>>>(nm, c->n, c->W_full, c->resscale_kkt, mu,
                                                        c->scalars);
         c->launches += 2;
-        cudaError_t e5 = cudaStreamSynchronize(s);
-        cudaFree(d_zu);
-        if (e5 != cudaSuccess) return fail(IPXGPU_ERR_CUDA, cudaGetErrorString(e5));
+        IPXGPU_CUDA(cudaStreamSynchronize(s));
     } else {
         fill_kernel<<<grid, kBlock, 0, c->stream>>>(nm, c->W_full, 1.0);
         fill_kernel<<<grid_for(c, c->m), kBlock, 0, c->stream>>>(c->m, c->resscale_kkt, 1.0);
