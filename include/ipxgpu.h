@@ -58,6 +58,15 @@ void ipxgpu_default_options(ipxgpu_options* opt);
 const char* ipxgpu_last_error(void);
 int ipxgpu_device_count(int* count);
 
+/* Starts creating the CUDA runtime and the context of `device` (-1: env
+ * IPXGPU_DEVICE, else driver initialisation only) on a helper thread and
+ * returns at once; ipxgpu_create joins it after its host-side layout work.
+ * Context creation takes 0.7-5 s in a fresh process: calling this when the
+ * library is loaded hides it behind model loading (the drop-in build of IPX
+ * does, see ipx_b200/host/gpu_bridge.cc). Idempotent. No reference
+ * counterpart (the reference needs no device). */
+int ipxgpu_warmup(int32_t device);
+
 /* Creates a context for the solver-form matrix AI = [A I] (m rows, n+m
  * columns, CSC, sorted row indices), i.e. Model::AI() (reference
  * src/model.h:61). Uploads this shard's structural columns in CSC and CSR

@@ -34,7 +34,7 @@ class CrResult(C.Structure):
 
 INTERRUPT_FN = C.CFUNCTYPE(i64, C.c_void_p)
 
-EXPORTS = ("ipxgpu_default_options ipxgpu_last_error ipxgpu_device_count ipxgpu_create "
+EXPORTS = ("ipxgpu_default_options ipxgpu_last_error ipxgpu_device_count ipxgpu_warmup ipxgpu_create "
            "ipxgpu_destroy ipxgpu_get_layout ipxgpu_get_tiling ipxgpu_synchronize ipxgpu_partition_columns ipxgpu_comm_unique_id "
            "ipxgpu_comm_init ipxgpu_normal_prepare ipxgpu_normal_prepare_dev ipxgpu_normal_apply "
            "ipxgpu_normal_apply_dev ipxgpu_diag_factorize ipxgpu_diag_get ipxgpu_diag_set "

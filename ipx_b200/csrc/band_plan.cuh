@@ -75,13 +75,9 @@ static void free_band(BandDev* T) {
     *T = BandDev();
 }
 
-// Builds the row streams of plan T->plan for a compressed structure and
-// uploads them. IPXGPU_ERR_UNSUPPORTED: the structure does not suit the banded
-// sweep (long runs, or more than max_pad padding); T is left empty.
-static int build_band(ipxgpu_ctx* c, BandDev* T, const int* ptr, const int* idx,
-                      const double* val, double max_pad) {
-    BandHost H;
-    if (!band_build(T->plan, ptr, idx, val, &H)) return IPXGPU_ERR_UNSUPPORTED;
+// Uploads host-built row streams. IPXGPU_ERR_UNSUPPORTED: more than max_pad padding (the
+// structure does not suit the banded sweep); T is left empty.
+static int upload_band(ipxgpu_ctx* c, BandDev* T, const BandHost& H, double max_pad) {
     if (H.rows > 0 && (double)H.pad_entries > max_pad * 32.0 * (double)H.rows)
         return IPXGPU_ERR_UNSUPPORTED;
     cudaStream_t s = c->stream;

@@ -7,7 +7,9 @@
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
+#include <mutex>
 #include <new>
+#include <thread>
 
 #include "context.cuh"
 #include "cr_kernels.cuh"
@@ -591,6 +593,63 @@ void ipxgpu_default_options(ipxgpu_options* opt) {
 
 const char* ipxgpu_last_error(void) { return g_last_error.c_str(); }
 
+// CUDA runtime and device context creation take 0.7-5 s in a fresh process. It runs on a helper
+// thread so that host-side work (model loading, layout builds) overlaps it; whoever needs the
+// device first joins the thread.
+namespace {
+struct Warmup {
+    std::mutex mu;
+    std::thread th;
+    bool started = false, joined = false;
+    int device = -1, ndev = 0;
+    cudaError_t err = cudaSuccess;
+    double ms = 0.0;
+    ~Warmup() {
+        if (th.joinable()) th.join();
+    }
+    void start(int dev_hint) {
+        std::lock_guard<std::mutex> lock(mu);
+        if (started) return;
+        started = true;
+        th = std::thread([this, dev_hint] {
+            const auto t0 = std::chrono::steady_clock::now();
+            err = cudaGetDeviceCount(&ndev);
+            if (err == cudaSuccess && ndev > 0) {
+                // Without a device hint only the driver is initialised here: the caller's
+                // current device is a property of ITS thread, resolved in ipxgpu_create.
+                int dev = dev_hint;
+                if (dev < 0) {
+                    const char* env = std::getenv("IPXGPU_DEVICE");
+                    if (env) dev = std::atoi(env);
+                }
+                device = dev;
+                if (dev >= 0 && dev < ndev) {
+                    err = cudaSetDevice(dev);
+                    if (err == cudaSuccess) err = cudaFree(nullptr);  // creates the context
+                }
+            }
+            ms = 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        });
+    }
+    void wait() {
+        std::lock_guard<std::mutex> lock(mu);
+        if (started && !joined) {
+            if (th.joinable()) th.join();
+            joined = true;
+        }
+    }
+};
+Warmup& warmup() {
+    static Warmup w;
+    return w;
+}
+}  // namespace
+
+int ipxgpu_warmup(int32_t device) {
+    warmup().start(device);
+    return IPXGPU_OK;
+}
+
 int ipxgpu_device_count(int* count) {
     if (!count) return fail(IPXGPU_ERR_ARGUMENT, "null count");
     *count = 0;
@@ -670,20 +729,133 @@ int ipxgpu_create(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp, co
     if (opt.nranks < 1 || opt.rank < 0 || opt.rank >= opt.nranks)
         return fail(IPXGPU_ERR_ARGUMENT, "invalid rank/nranks");
 
+    // ---- host-only part: runs while the helper thread creates the CUDA context ----
     const auto t_enter = std::chrono::steady_clock::now();
-    int ndev = 0;
-    cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e != cudaSuccess || ndev == 0)
+    warmup().start(opt.device);  // no-op when ipxgpu_warmup was called earlier in the process
+    const bool timing = std::getenv("IPXGPU_TIMING") != nullptr;
+    auto t_last = t_enter;
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[ipxgpu_create] %-34s %8.1f ms\n", what,
+                1e3 * std::chrono::duration<double>(now - t_last).count());
+        t_last = now;
+    };
+
+    // Column shard: explicit, or balanced by nonzeros.
+    int64_t cb = opt.col_begin, ce = opt.col_end;
+    if (cb < 0 || ce < 0) {
+        std::vector<int64_t> bounds((size_t)opt.nranks + 1);
+        IPXGPU_TRY(ipxgpu_partition_columns(n, AIp, opt.nranks, bounds.data()));
+        cb = bounds[opt.rank];
+        ce = bounds[opt.rank + 1];
+    }
+    if (cb < 0 || ce < cb || ce > n) return fail(IPXGPU_ERR_ARGUMENT, "invalid column range");
+    const int64_t nloc = ce - cb;
+    const int64_t base = AIp[cb];
+    const int64_t nnz = AIp[ce] - base;
+    if (nnz >= (int64_t)INT32_MAX || nloc >= (int64_t)INT32_MAX || m >= (int64_t)INT32_MAX)
+        return fail(IPXGPU_ERR_UNSUPPORTED, "shard exceeds int32 index range; use more shards");
+
+    // The band layouts are planned for the SM count of a B200 while the device is not known
+    // yet, and re-planned in the (not expected) case that the device reports another count.
+    const char* env_sms = std::getenv("IPXGPU_NUM_SMS");
+    const int spec_sms = env_sms ? std::max(1, std::atoi(env_sms)) : 148;
+    const char* env_sweep = std::getenv("IPXGPU_SWEEP");
+    const std::string how = env_sweep ? env_sweep : "auto";
+    const bool force = how == "band" || how == "tiled";
+    const double ratio = force ? 1e30 : 1.5;
+    const double max_pad = force ? 1.0 : 0.25;
+    const bool want_band = how != "generic" && nnz > 0 && m > 0;
+
+    int64_t pc = opt.panel_cols > 0 ? opt.panel_cols : (int64_t)2 << 20;
+    const char* env_pc = std::getenv("IPXGPU_PANEL_COLS");
+    if (opt.panel_cols <= 0 && env_pc) pc = std::max<int64_t>(1, std::atoll(env_pc));
+    const int npanels = (int)std::max<int64_t>(1, (nloc + pc - 1) / pc);
+
+    std::vector<int> cp, ci, rp, rj;  // shard CSC (int32) and, when needed, the full-shard CSR
+    std::vector<double> rx;
+    struct BandJob {  // declared after the vectors its thread reads: joined before they die
+        BandPlan plan;
+        BandHost H;
+        bool planned = false, built = false, oom = false;
+        std::thread th;
+    } job1, job2;
+    struct Joiner {
+        BandJob *a, *b;
+        ~Joiner() {
+            if (a->th.joinable()) a->th.join();
+            if (b->th.joinable()) b->th.join();
+        }
+    } joiner{&job1, &job2};
+
+    bool have_csr = false;
+    try {
+        cp.resize((size_t)nloc + 1);
+        ci.resize((size_t)nnz);
+        for (int64_t j = 0; j <= nloc; j++) cp[j] = (int)(AIp[cb + j] - base);
+        for (int64_t p = 0; p < nnz; p++) {
+            const int64_t i = AIi[base + p];
+            if (i < 0 || i >= m) return fail(IPXGPU_ERR_ARGUMENT, "row index out of range");
+            ci[p] = (int)i;
+        }
+        lap("host: CSC int32");
+        auto run_job = [&](BandJob* job, const int* ptr, const int* idx, const double* val) {
+            job->th = std::thread([=] {
+                try {
+                    job->built = band_build(job->plan, ptr, idx, val, &job->H);
+                } catch (const std::bad_alloc&) {
+                    job->oom = true;
+                }
+            });
+        };
+        if (want_band) {
+            job1.planned = plan_band(&job1.plan, (int)m, (int)nloc, nnz, spec_sms, ratio);
+            job2.planned = plan_band(&job2.plan, (int)nloc, (int)m, nnz, spec_sms, ratio);
+        }
+        if (job1.planned) run_job(&job1, cp.data(), ci.data(), AIx + base);
+        if (job2.planned || npanels == 1) {
+            // full-shard CSR (rows ascending, columns ascending within a row)
+            rp.assign((size_t)m + 1, 0);
+            rj.resize((size_t)nnz);
+            rx.resize((size_t)nnz);
+            for (int64_t p = 0; p < nnz; p++) rp[ci[p] + 1]++;
+            for (int64_t i = 0; i < m; i++) rp[i + 1] += rp[i];
+            std::vector<int> next(rp.begin(), rp.end() - 1);
+            for (int j = 0; j < (int)nloc; j++)
+                for (int p = cp[j]; p < cp[j + 1]; p++) {
+                    const int put = next[ci[p]]++;
+                    rj[put] = j;
+                    rx[put] = AIx[base + p];
+                }
+            have_csr = true;
+            lap("host: CSR of the shard");
+            if (job2.planned) run_job(&job2, rp.data(), rj.data(), rx.data());
+        }
+    } catch (const std::bad_alloc&) {
+        return fail(IPXGPU_ERR_OUT_OF_MEMORY, "host allocation failed while building layouts");
+    }
+
+    // ---- device part ----
+    Warmup& wu = warmup();
+    wu.wait();
+    lap("wait for CUDA runtime / context");
+    if (timing)
+        fprintf(stderr, "[ipxgpu_create] %-34s %8.1f ms (helper thread)\n",
+                "CUDA runtime / context creation", wu.ms);
+    if (wu.err != cudaSuccess || wu.ndev == 0)
         return fail(IPXGPU_ERR_CUDA, std::string("no CUDA device (libipxgpu has no CPU path): ") +
-                                         cudaGetErrorString(e));
+                                         cudaGetErrorString(wu.err));
+    const int ndev = wu.ndev;
     int device = opt.device;
     if (device < 0) {
         const char* env = std::getenv("IPXGPU_DEVICE");
         if (env) device = std::atoi(env);
         else IPXGPU_CUDA(cudaGetDevice(&device));
     }
-    if (device >= ndev) return fail(IPXGPU_ERR_ARGUMENT, "device ordinal out of range");
+    if (device < 0 || device >= ndev) return fail(IPXGPU_ERR_ARGUMENT, "device ordinal out of range");
     IPXGPU_CUDA(cudaSetDevice(device));
+    IPXGPU_CUDA(cudaFree(nullptr));  // this device's context, if the helper warmed another one
 
     ipxgpu_ctx* c = new (std::nothrow) ipxgpu_ctx;
     if (!c) return fail(IPXGPU_ERR_OUT_OF_MEMORY, "host allocation failed");
@@ -706,63 +878,22 @@ int ipxgpu_create(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp, co
         IPXGPU_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         c->own_stream = true;
     }
-
-    // Column shard: explicit, or balanced by nonzeros.
-    int64_t cb = opt.col_begin, ce = opt.col_end;
-    if (cb < 0 || ce < 0) {
-        std::vector<int64_t> bounds((size_t)opt.nranks + 1);
-        IPXGPU_TRY(ipxgpu_partition_columns(n, AIp, opt.nranks, bounds.data()));
-        cb = bounds[opt.rank];
-        ce = bounds[opt.rank + 1];
-    }
-    if (cb < 0 || ce < cb || ce > n) return fail(IPXGPU_ERR_ARGUMENT, "invalid column range");
     c->col_begin = cb;
     c->col_end = ce;
-    const int64_t nloc = ce - cb;
-    const int64_t base = AIp[cb];
-    const int64_t nnz = AIp[ce] - base;
-    if (nnz >= (int64_t)INT32_MAX || nloc >= (int64_t)INT32_MAX || m >= (int64_t)INT32_MAX)
-        return fail(IPXGPU_ERR_UNSUPPORTED, "shard exceeds int32 index range; use more shards");
     c->nloc = (int)nloc;
     c->csc.nseg = (int)nloc;
     c->csc.nnz = nnz;
 
     cudaStream_t s = c->stream;
-    const bool timing = std::getenv("IPXGPU_TIMING") != nullptr;
-    IPXGPU_CUDA(cudaFree(nullptr));  // forces the device context into existence here
-    auto t_last = std::chrono::steady_clock::now();
-    if (timing)
-        fprintf(stderr, "[ipxgpu_create] %-28s %8.1f ms\n", "CUDA runtime / context",
-                1e3 * std::chrono::duration<double>(t_last - t_enter).count());
-    auto lap = [&](const char* what) {
-        if (!timing) return;
-        const auto now = std::chrono::steady_clock::now();
-        fprintf(stderr, "[ipxgpu_create] %-28s %8.1f ms\n", what,
-                1e3 * std::chrono::duration<double>(now - t_last).count());
-        t_last = now;
-    };
     try {
-        // Shard CSC with int32 indices.
-        std::vector<int> cp(nloc + 1), ci((size_t)nnz);
-        for (int64_t j = 0; j <= nloc; j++) cp[j] = (int)(AIp[cb + j] - base);
-        for (int64_t p = 0; p < nnz; p++) {
-            const int64_t i = AIi[base + p];
-            if (i < 0 || i >= m) return fail(IPXGPU_ERR_ARGUMENT, "row index out of range");
-            ci[p] = (int)i;
-        }
         IPXGPU_TRY(upload(&c->csc.ptr, cp, s));
         IPXGPU_TRY(upload(&c->csc.idx, ci, s));
         IPXGPU_TRY(dev_alloc(&c->csc.val, (size_t)nnz));
         if (nnz > 0)
             IPXGPU_CUDA(cudaMemcpyAsync(c->csc.val, AIx + base, sizeof(double) * nnz,
                                         cudaMemcpyHostToDevice, s));
-
-        lap("CSC int32 + upload");
+        lap("upload CSC");
         // Panels: t-slice of at most panel_cols columns (default 2M = 16 MB).
-        int64_t pc = opt.panel_cols > 0 ? opt.panel_cols : (int64_t)2 << 20;
-        const char* env_pc = std::getenv("IPXGPU_PANEL_COLS");
-        if (opt.panel_cols <= 0 && env_pc) pc = std::max<int64_t>(1, std::atoll(env_pc));
-        const int npanels = (int)std::max<int64_t>(1, (nloc + pc - 1) / pc);
         // A shard without structural columns still gets one (empty) panel: its
         // row sweep carries the slack term and the fused dot product.
         c->panels.resize(npanels);
@@ -776,26 +907,32 @@ int ipxgpu_create(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp, co
             // CSR of the panel (rows global, columns local to the shard,
             // ascending within a row).
             const int64_t q0 = cp[P.c0], q1 = cp[P.c1];
-            std::vector<int> rp((size_t)m + 1, 0);
-            for (int64_t p = q0; p < q1; p++) rp[ci[p] + 1]++;
-            for (int64_t i = 0; i < m; i++) rp[i + 1] += rp[i];
-            std::vector<int> rj((size_t)(q1 - q0));
-            std::vector<double> rx((size_t)(q1 - q0));
-            {
-                std::vector<int> next(rp.begin(), rp.end() - 1);
+            std::vector<int> prp, prj;
+            std::vector<double> prx;
+            const bool whole = npanels == 1 && have_csr;
+            if (!whole) {
+                prp.assign((size_t)m + 1, 0);
+                for (int64_t p = q0; p < q1; p++) prp[ci[p] + 1]++;
+                for (int64_t i = 0; i < m; i++) prp[i + 1] += prp[i];
+                prj.resize((size_t)(q1 - q0));
+                prx.resize((size_t)(q1 - q0));
+                std::vector<int> next(prp.begin(), prp.end() - 1);
                 for (int j = P.c0; j < P.c1; j++)
                     for (int p = cp[j]; p < cp[j + 1]; p++) {
                         const int put = next[ci[p]]++;
-                        rj[put] = j;
-                        rx[put] = AIx[base + p];
+                        prj[put] = j;
+                        prx[put] = AIx[base + p];
                     }
             }
+            const std::vector<int>& urp = whole ? rp : prp;
+            const std::vector<int>& urj = whole ? rj : prj;
+            const std::vector<double>& urx = whole ? rx : prx;
             P.csr.nseg = (int)m;
             P.csr.nnz = q1 - q0;
-            IPXGPU_TRY(upload(&P.csr.ptr, rp, s));
-            IPXGPU_TRY(upload(&P.csr.idx, rj, s));
-            IPXGPU_TRY(upload(&P.csr.val, rx, s));
-            HostTiles rt = build_tiles(rp.data(), 0, (int)m, 0);
+            IPXGPU_TRY(upload(&P.csr.ptr, urp, s));
+            IPXGPU_TRY(upload(&P.csr.idx, urj, s));
+            IPXGPU_TRY(upload(&P.csr.val, urx, s));
+            HostTiles rt = build_tiles(urp.data(), 0, (int)m, 0);
             IPXGPU_TRY(upload_tiles(&P.row_tiles, rt, s));
             max_grid = std::max(max_grid, std::max(P.col_tiles.ntiles, P.row_tiles.ntiles));
             IPXGPU_CUDA(cudaStreamSynchronize(s));  // host vectors die here
@@ -804,59 +941,41 @@ int ipxgpu_create(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp, co
         // Banded shared-memory sweeps (band_sweep.cuh) carry the normal-matrix
         // apply wherever the structure suits them. IPXGPU_SWEEP=generic turns
         // them off, IPXGPU_SWEEP=band forces them whenever a plan fits.
-        {
-            const char* env = std::getenv("IPXGPU_SWEEP");
-            const std::string how = env ? env : "auto";
-            const bool force = how == "band" || how == "tiled";
-            const double ratio = force ? 1e30 : 1.5;
-            const double max_pad = force ? 1.0 : 0.25;
-            if (how != "generic" && nnz > 0 && m > 0) {
-                BandPlan plan;
-                if (plan_band(&plan, (int)m, (int)nloc, nnz, c->num_sms, ratio)) {
-                    c->band1 = new BandDev();
-                    c->band1->plan = plan;
-                    const int rc1 = build_band(c, c->band1, cp.data(), ci.data(), AIx + base,
-                                               max_pad);
-                    lap("band layout sweep 1");
-                    if (rc1 == IPXGPU_ERR_UNSUPPORTED) {  // structure suits the generic sweep
-                        free_band(c->band1);
-                        delete c->band1;
-                        c->band1 = nullptr;
-                    } else {
-                        IPXGPU_TRY(rc1);
-                        max_grid = std::max(max_grid, plan.nitems);
-                    }
-                }
-                if (plan_band(&plan, (int)nloc, (int)m, nnz, c->num_sms, ratio)) {
-                    // full-shard CSR (rows ascending, columns ascending within a row)
-                    std::vector<int> rp((size_t)m + 1, 0), rj((size_t)nnz);
-                    std::vector<double> rx((size_t)nnz);
-                    for (int64_t p = 0; p < nnz; p++) rp[ci[p] + 1]++;
-                    for (int64_t i = 0; i < m; i++) rp[i + 1] += rp[i];
-                    std::vector<int> next(rp.begin(), rp.end() - 1);
-                    for (int j = 0; j < (int)nloc; j++)
-                        for (int p = cp[j]; p < cp[j + 1]; p++) {
-                            const int put = next[ci[p]]++;
-                            rj[put] = j;
-                            rx[put] = AIx[base + p];
-                        }
-                    lap("CSR for sweep 2");
-                    c->band2 = new BandDev();
-                    c->band2->plan = plan;
-                    const int rc2 = build_band(c, c->band2, rp.data(), rj.data(), rx.data(),
-                                               max_pad);
-                    lap("band layout sweep 2");
-                    if (rc2 == IPXGPU_ERR_UNSUPPORTED) {
-                        free_band(c->band2);
-                        delete c->band2;
-                        c->band2 = nullptr;
-                    } else {
-                        IPXGPU_TRY(rc2);
-                        max_grid = std::max(max_grid, plan.nitems);
-                    }
-                }
+        if (job1.th.joinable()) job1.th.join();
+        if (job2.th.joinable()) job2.th.join();
+        lap("wait for the band layouts");
+        if (job1.oom || job2.oom)
+            return fail(IPXGPU_ERR_OUT_OF_MEMORY, "host allocation failed while building layouts");
+        if (want_band && c->num_sms != spec_sms) {  // not a B200: plan again for this device
+            for (int k = 0; k < 2; k++) {
+                BandJob& job = k == 0 ? job1 : job2;
+                job.H = BandHost();
+                job.built = false;
+                job.planned = k == 0 ? plan_band(&job.plan, (int)m, (int)nloc, nnz, c->num_sms, ratio)
+                                     : plan_band(&job.plan, (int)nloc, (int)m, nnz, c->num_sms, ratio);
+                if (!job.planned || (k == 1 && !have_csr)) continue;
+                job.built = k == 0 ? band_build(job.plan, cp.data(), ci.data(), AIx + base, &job.H)
+                                   : band_build(job.plan, rp.data(), rj.data(), rx.data(), &job.H);
             }
+            lap("band layouts re-planned");
         }
+        for (int k = 0; k < 2; k++) {
+            BandJob& job = k == 0 ? job1 : job2;
+            if (!job.planned || !job.built) continue;  // structure suits the generic sweep
+            BandDev* T = new BandDev();
+            T->plan = job.plan;
+            const int rc = upload_band(c, T, job.H, max_pad);
+            job.H = BandHost();
+            if (rc != IPXGPU_OK) {
+                free_band(T);
+                delete T;
+                if (rc == IPXGPU_ERR_UNSUPPORTED) continue;
+                return rc;
+            }
+            (k == 0 ? c->band1 : c->band2) = T;
+            max_grid = std::max(max_grid, job.plan.nitems);
+        }
+        lap("upload band layouts");
         IPXGPU_TRY(dev_alloc(&c->t, (size_t)nloc));
         IPXGPU_TRY(dev_alloc(&c->xin, (size_t)m));
         IPXGPU_TRY(dev_alloc(&c->ybuf, (size_t)m + 1));

@@ -68,6 +68,17 @@ ModelEntry* EntryOfContext(ipxgpu_ctx* ctx) {
     return nullptr;
 }
 
+// The CUDA context is created on a helper thread from the moment the drop-in build of IPX is
+// loaded, so that it is ready (or well under way) when the first KKTSolverDiag::Factorize needs
+// it. IPXGPU_EAGER_INIT=0 defers it to the first context.
+const bool g_eager_init = [] {
+    const char* env = std::getenv("IPXGPU_EAGER_INIT");
+    if (env && std::atoi(env) == 0) return false;
+    const char* dev = std::getenv("IPXGPU_DEVICE");
+    ipxgpu_warmup(dev ? std::atoi(dev) : 0);
+    return true;
+}();
+
 size_t MaxContexts() {
     const char* env = std::getenv("IPXGPU_MAX_CONTEXTS");
     const long v = env ? std::atol(env) : 4;

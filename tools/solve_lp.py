@@ -41,13 +41,18 @@ ap.add_argument("--stop-at-switch", type=int, default=0,
 ap.add_argument("--out", default=None)
 args = ap.parse_args()
 
+# Libraries first, as an application would link them: the drop-in build starts creating its
+# CUDA context when it is loaded (IPXGPU_EAGER_INIT=0 turns that off).
+libs = {impl: ipxlib.IpxLibrary(path)
+        for impl, path in (("ref", ipxlib.REF_LIB), ("gpu", ipxlib.GPU_LIB))
+        if args.impl in ("both", impl)}
 lp = make(args.lp)
 print(f"LP {lp.name}: m={lp.m} n={lp.n} nnz={lp.nnz} optimum={lp.optimum}", flush=True)
 results = {}
 for impl, path in (("ref", ipxlib.REF_LIB), ("gpu", ipxlib.GPU_LIB)):
     if args.impl not in ("both", impl):
         continue
-    lib = ipxlib.IpxLibrary(path)
+    lib = libs[impl]
     s = lib.lp_solver()
     s.set_parameters(display=int(os.environ.get("IPX_DISPLAY", "0")), dualize=0,
                      crossover=args.crossover, switchiter=args.switchiter,
