@@ -307,14 +307,22 @@ pcr_fused_kernel(FusedArgs F) {
             }
             __syncthreads();
             for (int i = i0 + tid; i < i1; i += nthr) {
+                // All peers' loads go out before the first sum waits (one NVLink round
+                // trip per group of 8 ranks instead of one per rank); summed in rank order.
                 double yv = 0.0;
-                for (int r = 0; r < F.nranks; r++) {
-                    double part;
-                    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];"
-                                 : "=d"(part)
-                                 : "l"(F.peers[r] + off + i)
-                                 : "memory");
-                    yv += part;
+                for (int rb = 0; rb < F.nranks; rb += 8) {
+                    double part[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        part[u] = 0.0;
+                        if (rb + u < F.nranks)
+                            asm volatile("ld.relaxed.sys.global.f64 %0, [%1];"
+                                         : "=d"(part[u])
+                                         : "l"(F.peers[rb + u] + off + i));
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        if (rb + u < F.nranks) yv += part[u];
                 }
                 lhs[i] = yv;
                 dot += __dmul_rn(x[i], yv);
