@@ -106,13 +106,26 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+STRONG = False        # --workload c5: one fixed LP (config 5) column-sharded over the ranks
+
+
+def set_workload(name):
+    """c2 (default): BASELINE.json configs[1], weak scaling (one 1M-column shard per GPU).
+    c5: configs[4], 1M x 20M with 100M nonzeros, strong scaling (nnz-balanced column shards)."""
+    global M_ROWS, N_COLS, NNZ_PER_COL, SEED, STRONG
+    if name == "c5":
+        M_ROWS, N_COLS, NNZ_PER_COL, SEED, STRONG = 1_000_000, 20_000_000, 5, 1005, True
+
+
 def make_lp(world):
     from ipx_b200 import lpgen
-    return lpgen.random_sparse_lp(M_ROWS, N_COLS * world, NNZ_PER_COL, SEED)
+    ncols = N_COLS if STRONG else N_COLS * world
+    return lpgen.random_sparse_lp(M_ROWS, ncols, NNZ_PER_COL, SEED)
 
 
 def workload_name(world):
-    return (f"synthetic sparse LP {M_ROWS} rows x {N_COLS * world} cols, {NNZ_PER_COL} nnz/col, "
+    ncols = N_COLS if STRONG else N_COLS * world
+    return (f"synthetic sparse LP {M_ROWS} rows x {ncols} cols, {NNZ_PER_COL} nnz/col, "
             f"KKTSolverDiag diagonal-preconditioned CR, {ITERS} iterations per step")
 
 
@@ -204,7 +217,8 @@ def run_gpu(args):
     resscale = 1.0 / np.sqrt(W[n:])
 
     # This rank's column shard: a contiguous 1M-column slice.
-    c0, c1 = N_COLS * rank, N_COLS * (rank + 1)
+    # (--workload c5: nnz-balanced shards of the one LP, chosen by the library.)
+    c0, c1 = (-1, -1) if STRONG else (N_COLS * rank, N_COLS * (rank + 1))
     stream = torch.cuda.Stream(device=dev)  # the library launches on this stream
     torch.cuda.set_stream(stream)
     ctx = capi.Context(m, n, AIp, AIi, AIx, device=local_rank, rank=rank, nranks=world,
@@ -288,8 +302,10 @@ def run_gpu(args):
         t_dev, t_e2e, t_op = tt.tolist()
 
     total_applies = applies_per_step * args.steps
-    value = world * total_applies / t_dev
-    e2e = world * total_applies / t_e2e
+    # weak scaling: every rank applies its own 1M-column shard; strong: one apply of the LP
+    units = 1 if STRONG else world
+    value = units * total_applies / t_dev
+    e2e = units * total_applies / t_e2e
 
     # Roofline of the A*D^2*A' apply (sweep 1 + sweep 2) from the device timers
     # inside the timed CR loops: algorithmic bytes of this rank's shard per apply.
@@ -301,21 +317,35 @@ def run_gpu(args):
     achieved = bytes_apply / t_apply / 1e9
     iso = ctx.time_normal_apply(20, flush_l2=True) if world == 1 else None
 
+    tiling = ctx.tiling()
+    banded = bool(tiling["sweep1"]["enabled"] and tiling["sweep2"]["enabled"])
+    if not banded:
+        kernel_name = ("seg_sweep_kernel<OpColDotScale> + seg_sweep_kernel<OpRowGather> (generic "
+                       "sweeps: the banded layout does not fit this shape)")
+    elif world == 1 or os.environ.get("IPXGPU_PEER", "1") != "0":
+        kernel_name = ("pcr_fused_kernel (persistent CR solve): banded sweep 1 + sweep 2 + combine "
+                       "stages of one A*D^2*A' apply")
+    else:
+        kernel_name = "band_sweep_kernel (sweep 1) + band_sweep_kernel (sweep 2) + band_combine_kernel"
+    if world == 1:
+        collective = "none"
+    elif banded and os.environ.get("IPXGPU_PEER", "1") != "0":
+        collective = ("in-kernel sum of the ranks' partial products over NVLink peer memory "
+                      "(P2P loads, per-slice flags) once per CR iteration")
+    else:
+        collective = "ncclAllReduce(m+1 f64) per CR iteration"
     line = None
     if rank == 0:
         line = {
             "metric": "cr_matvecs_per_sec", "value": value, "unit": "matvec/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_dev / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if STRONG else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(world), "rows": m, "cols": n,
-                       "nnz": int(lp.nnz), "cols_per_gpu": N_COLS,
-                       "l2": "inputs larger than L2 (240 MB of matrix data per apply)",
-                       "collective": "none" if world == 1 else (
-                           "in-kernel sum of the ranks' partial products over NVLink peer memory "
-                           "(P2P loads, per-slice flags) once per CR iteration"
-                           if os.environ.get("IPXGPU_PEER", "1") != "0"
-                           else "ncclAllReduce(m+1 f64) per CR iteration")},
+                       "nnz": int(lp.nnz), "cols_per_gpu": int(ncols_local),
+                       "l2": f"inputs larger than L2 ({24 * nnz_local / 1e6:.0f} MB of matrix data "
+                             "per apply and GPU)",
+                       "collective": collective},
             "e2e": {"value": e2e, "unit": "matvec/s",
                     "h2d_bytes_per_step": 16 * m, "d2h_bytes_per_step": 8 * m},
             "gpu_launches": int(launches),
@@ -325,13 +355,10 @@ def run_gpu(args):
                          # 6 iterations = 7 applies: 2051.9 MB read + 30.7 MB written) / 7, from
                          # the ncu --set full capture profiles/r01b_ncu_full_band_fused.csv;
                          # only valid for the 1-GPU C2 workload.
-                         "traffic": NCU_TRAFFIC_BYTES_PER_APPLY if world == 1 else None,
+                         "traffic": NCU_TRAFFIC_BYTES_PER_APPLY if world == 1 and not STRONG else None,
                          "traffic_source": "profiles/r01b_ncu_full_band_fused.csv",
                          "peak_source": peak_src,
-                         "kernel": ("pcr_fused_kernel (persistent CR solve): banded sweep 1 + sweep 2 "
-                                    "+ combine stages of one A*D^2*A' apply") if world == 1 else
-                                   "band_sweep_kernel (sweep 1) + band_sweep_kernel (sweep 2) + "
-                                   "band_combine_kernel",
+                         "kernel": kernel_name,
                          "algorithmic_bytes_per_apply": bytes_apply,
                          "apply_us_in_loop": 1e6 * t_apply,
                          "apply_us_isolated_l2_flushed": 1e3 * iso["apply_ms"] if iso else None,
@@ -341,7 +368,7 @@ def run_gpu(args):
         }
     ctx.close()
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not STRONG:
         # Bounded CPU sample of the same workload: ~20 applies on one core.
         lp1 = lp
         step, kind = cpu_reference_rate(lp1, W, rhs, resscale, 9, 1)
@@ -365,7 +392,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
+                    help="c2: BASELINE.json configs[1] (the headline metric; weak scaling); "
+                         "c5: configs[4], 1M x 20M, 100M nnz (strong scaling; not the headline)")
     args = ap.parse_args()
+    set_workload(args.workload)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -84,7 +84,9 @@ void ipxgpu_destroy(ipxgpu_ctx* ctx);
  *        csr_tiles]. */
 int ipxgpu_get_layout(ipxgpu_ctx* ctx, int64_t out[8]);
 /* Tiling of the two sweeps of the normal-matrix apply, 8 values per sweep:
- * [enabled, VB, SB, NVB, NSB, K, nparts, nitems] (sweep 1, then sweep 2). */
+ * [enabled, VB, SB, NVB, NSB, K, nparts, nitems] (sweep 1, then sweep 2).
+ * enabled: 0 = generic sweep, 1 = banded sweep, 2 = banded sweep plus a
+ * generic sweep over the dense segments (rows / columns) it leaves out. */
 int ipxgpu_get_tiling(ipxgpu_ctx* ctx, int64_t out[16]);
 int ipxgpu_synchronize(ipxgpu_ctx* ctx);
 

@@ -42,6 +42,7 @@ constexpr int kBandMaxVB = 32768;        // 15-bit band index
 constexpr unsigned kBandLast = 0x8000u;  // key flag: last entry of its run
 constexpr int kBandRowBytes = 384;       // 32 keys + 32 values
 constexpr int kBandMaxSteps = 256;       // bands per item (row table in shared memory)
+constexpr int kBandMaxRun = 64;          // longest run of a segment inside one tile
 constexpr int kBandTailRows = 64;        // spare rows after the last one (>= 3*D)
 
 struct BandPlan {
@@ -396,7 +397,9 @@ band_sweep_kernel(BandDev T, BandArgs A, int mode, Reduce red, CrState* st) {
         if (grid_reduce(red, mine, 0.0, 0.0, s_red, &s_flag, &ts, &ts2, &tm) &&
             threadIdx.x == 0) {
             A.out[T.plan.S] = ts;
-            if (st) after_apply(st, A.apply_mode, ts, A.slot);
+            // (plain, no slot): the scalar step and the time stamp belong to a later kernel
+            if (st && !(A.apply_mode == kApplyPlain && A.slot == kSlotNone))
+                after_apply(st, A.apply_mode, ts, A.slot);
         }
     }
 }
@@ -427,7 +430,8 @@ band_combine_kernel(BandDev T, BandArgs A, int mode, Reduce red, CrState* st) {
         if (grid_reduce(red, mine, 0.0, 0.0, s_red, &s_flag, &ts, &ts2, &tm) &&
             threadIdx.x == 0) {
             A.out[S] = ts;
-            if (st) after_apply(st, A.apply_mode, ts, A.slot);
+            if (st && !(A.apply_mode == kApplyPlain && A.slot == kSlotNone))
+                after_apply(st, A.apply_mode, ts, A.slot);
         }
     }
 }
@@ -456,10 +460,40 @@ inline bool band_finish_plan(BandPlan* P) {
 // Re-tiles a compressed structure (segments ptr[0..S], gather indices idx in
 // [0,V), ascending per segment) into the banded row streams. Returns false when
 // a run is longer than max_run (such structures suit the generic sweep).
+//
+// `spilled` (optional): instead of refusing, segments with such a run are left out of the
+// streams altogether (their accumulators stay 0) and listed, ascending; the caller sweeps them
+// with the generic kernel (dense rows / columns of an otherwise well-spread matrix). Refuses
+// when the spilled segments hold more than 3/4 of the entries.
 inline bool band_build(const BandPlan& P, const int* ptr, const int* idx, const double* val,
-                       BandHost* H, int max_run = 64) {
+                       BandHost* H, int max_run = kBandMaxRun, std::vector<int>* spilled = nullptr) {
     const int S = P.S, VB = P.VB, SB = P.SB, NVB = P.NVB, NSB = P.NSB, NW = P.NW;
     const size_t ntiles = (size_t)NSB * NVB;
+    std::vector<char> skip;
+    if (spilled) {
+        spilled->clear();
+        long long spilled_entries = 0;
+        for (int s = 0; s < S; s++) {
+            int p = ptr[s];
+            const int pe = ptr[s + 1];
+            bool is_long = false;
+            while (p < pe && !is_long) {
+                const int vb = idx[p] / VB;
+                int q = p + 1;
+                while (q < pe && idx[q] / VB == vb) q++;
+                is_long = q - p > max_run;
+                p = q;
+            }
+            if (is_long) {
+                if (skip.empty()) skip.assign((size_t)S, 0);
+                skip[s] = 1;
+                spilled->push_back(s);
+                spilled_entries += pe - ptr[s];
+            }
+        }
+        if (4 * spilled_entries > 3 * (long long)P.nnz) return false;
+    }
+    const bool any_skip = !skip.empty();
     struct Run {
         int first;            // first entry in idx/val
         unsigned short seg;   // local segment
@@ -472,6 +506,7 @@ inline bool band_build(const BandPlan& P, const int* ptr, const int* idx, const 
     const size_t ntw = ntiles * (size_t)NW;
     std::vector<long long> tcount(ntw + 1, 0);
     for (int s = 0; s < S; s++) {
+        if (any_skip && skip[s]) continue;
         const size_t trow = (size_t)(s / SB) * NVB;
         const int w = (s % SB) % NW;
         int p = ptr[s];
@@ -490,6 +525,7 @@ inline bool band_build(const BandPlan& P, const int* ptr, const int* idx, const 
     {
         std::vector<long long> next(tcount.begin(), tcount.end() - 1);
         for (int s = 0; s < S; s++) {
+            if (any_skip && skip[s]) continue;
             const size_t trow = (size_t)(s / SB) * NVB;
             const int w = (s % SB) % NW;
             int p = ptr[s];

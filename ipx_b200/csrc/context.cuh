@@ -72,6 +72,16 @@ struct Panel {
 };
 
 
+// Segments the banded layout of a sweep leaves out (dense rows / columns: runs longer than a
+// lane can carry): a compact compressed copy swept by the generic kernel right after the banded
+// one; map[k] = segment k's index in the full structure.
+struct Spill {
+    int nseg = 0;
+    DevMatrix A;
+    TileSet tiles;
+    int* map = nullptr;
+};
+
 template <class T>
 inline int dev_alloc(T** p, size_t count) {
     *p = nullptr;
@@ -152,6 +162,7 @@ struct ipxgpu_ctx {
     // banded shared-memory sweeps of the normal-matrix apply (may be null)
     ipxgpu::BandDev* band1 = nullptr;  // t = W .* (A'x): gather x, segments = columns
     ipxgpu::BandDev* band2 = nullptr;  // y = A t: gather t, segments = rows
+    ipxgpu::Spill spill1, spill2;      // segments left to the generic kernel (usually none)
 
     // peer exchange (NVLink P2P) of the persistent CR kernel for sharded contexts
     void* xchg = nullptr;             // own exchange buffer: y[2][xchg_mpad] doubles, then flags

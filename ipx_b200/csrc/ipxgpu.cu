@@ -179,6 +179,10 @@ static int launch_normal_apply_w(ipxgpu_ctx* c, const double* Wc, const double* 
     if (band1) {
         BandArgs a1{x, Wc, nullptr, nullptr, c->t, kApplyPlain, kSlotNone};
         IPXGPU_TRY(launch_band(c, *c->band1, a1, kBandColScale, st));
+        if (c->spill1.nseg > 0) {  // dense columns
+            OpColDotScaleSpill op{x, Wc, c->t, c->spill1.map};
+            IPXGPU_TRY(launch_sweep(c, op, c->spill1.tiles, c->spill1.A, st));
+        }
     }
     for (int k = 0; k < np; k++) {
         const Panel& P = c->panels[k];
@@ -200,9 +204,16 @@ static int launch_normal_apply_w(ipxgpu_ctx* c, const double* Wc, const double* 
         IPXGPU_TRY(launch_sweep(c, op2, P.row_tiles, P.csr, sharded ? nullptr : st));
     }
     if (band2) {
+        // With spilled (dense) rows the scalar step that follows the apply waits for them.
+        const bool spill = c->spill2.nseg > 0;
+        const int mode2 = sharded ? (int)kApplyPlain : mode;
         BandArgs a2{c->t, nullptr, (c->rank == 0) ? Ws : nullptr, x, y,
-                    sharded ? (int)kApplyPlain : mode, slot};
+                    spill ? (int)kApplyPlain : mode2, spill ? (int)kSlotNone : slot};
         IPXGPU_TRY(launch_band(c, *c->band2, a2, kBandRowFinal, sharded ? nullptr : st));
+        if (spill) {
+            OpRowGatherSpill op{c->t, x, y, c->spill2.map, (int)c->m, mode2, slot};
+            IPXGPU_TRY(launch_sweep(c, op, c->spill2.tiles, c->spill2.A, sharded ? nullptr : st));
+        }
     }
     if (sharded) {
         IPXGPU_TRY(allreduce_sum(c, y, (size_t)c->m + 1));
@@ -279,6 +290,7 @@ static inline void cpu_relax() {
 static bool fused_available(ipxgpu_ctx* c) {
     if ((c->nranks != 1 && !c->peers_ready) || !c->band1 || !c->band2 || c->m <= 0) return false;
     if (c->band1->plan.nparts != 1) return false;  // sweep 1 must write t directly
+    if (c->spill1.nseg > 0 || c->spill2.nseg > 0) return false;  // spilled segments: extra launches
     if (const char* env = std::getenv("IPXGPU_FUSED"))
         if (std::atoi(env) == 0) return false;
     return true;
@@ -686,6 +698,11 @@ void ipxgpu_destroy(ipxgpu_ctx* c) {
     dev_free(c->fused_red);
     if (c->band1) { free_band(c->band1); delete c->band1; }
     if (c->band2) { free_band(c->band2); delete c->band2; }
+    for (Spill* sp : {&c->spill1, &c->spill2}) {
+        free_matrix(&sp->A);
+        free_tiles(&sp->tiles);
+        dev_free(sp->map);
+    }
     free_matrix(&c->csc);
     for (Panel& P : c->panels) {
         free_tiles(&P.col_tiles);
@@ -778,6 +795,7 @@ int ipxgpu_create(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp, co
     struct BandJob {  // declared after the vectors its thread reads: joined before they die
         BandPlan plan;
         BandHost H;
+        std::vector<int> spilled;  // segments left to the generic kernel
         bool planned = false, built = false, oom = false;
         std::thread th;
     } job1, job2;
@@ -803,7 +821,8 @@ int ipxgpu_create(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp, co
         auto run_job = [&](BandJob* job, const int* ptr, const int* idx, const double* val) {
             job->th = std::thread([=] {
                 try {
-                    job->built = band_build(job->plan, ptr, idx, val, &job->H);
+                    job->built = band_build(job->plan, ptr, idx, val, &job->H, kBandMaxRun,
+                                            &job->spilled);
                 } catch (const std::bad_alloc&) {
                     job->oom = true;
                 }
@@ -954,8 +973,10 @@ int ipxgpu_create(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp, co
                 job.planned = k == 0 ? plan_band(&job.plan, (int)m, (int)nloc, nnz, c->num_sms, ratio)
                                      : plan_band(&job.plan, (int)nloc, (int)m, nnz, c->num_sms, ratio);
                 if (!job.planned || (k == 1 && !have_csr)) continue;
-                job.built = k == 0 ? band_build(job.plan, cp.data(), ci.data(), AIx + base, &job.H)
-                                   : band_build(job.plan, rp.data(), rj.data(), rx.data(), &job.H);
+                job.built = k == 0 ? band_build(job.plan, cp.data(), ci.data(), AIx + base, &job.H,
+                                                kBandMaxRun, &job.spilled)
+                                   : band_build(job.plan, rp.data(), rj.data(), rx.data(), &job.H,
+                                                kBandMaxRun, &job.spilled);
             }
             lap("band layouts re-planned");
         }
@@ -974,6 +995,35 @@ int ipxgpu_create(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp, co
             }
             (k == 0 ? c->band1 : c->band2) = T;
             max_grid = std::max(max_grid, job.plan.nitems);
+            if (!job.spilled.empty()) {
+                // compact copy of the spilled segments for the generic kernel
+                const int* ptr = k == 0 ? cp.data() : rp.data();
+                const int* idx = k == 0 ? ci.data() : rj.data();
+                const double* val = k == 0 ? AIx + base : rx.data();
+                Spill& sp = k == 0 ? c->spill1 : c->spill2;
+                const int ns = (int)job.spilled.size();
+                std::vector<int> sptr((size_t)ns + 1, 0);
+                for (int q = 0; q < ns; q++)
+                    sptr[q + 1] = sptr[q] + (ptr[job.spilled[q] + 1] - ptr[job.spilled[q]]);
+                std::vector<int> sidx((size_t)sptr[ns]);
+                std::vector<double> sval((size_t)sptr[ns]);
+                for (int q = 0; q < ns; q++) {
+                    const int p0 = ptr[job.spilled[q]], len = sptr[q + 1] - sptr[q];
+                    std::copy(idx + p0, idx + p0 + len, sidx.begin() + sptr[q]);
+                    std::copy(val + p0, val + p0 + len, sval.begin() + sptr[q]);
+                }
+                sp.nseg = ns;
+                sp.A.nseg = ns;
+                sp.A.nnz = sptr[ns];
+                IPXGPU_TRY(upload(&sp.A.ptr, sptr, s));
+                IPXGPU_TRY(upload(&sp.A.idx, sidx, s));
+                IPXGPU_TRY(upload(&sp.A.val, sval, s));
+                IPXGPU_TRY(upload(&sp.map, job.spilled, s));
+                HostTiles st = build_tiles(sptr.data(), 0, ns, 0);
+                IPXGPU_TRY(upload_tiles(&sp.tiles, st, s));
+                max_grid = std::max(max_grid, sp.tiles.ntiles);
+                IPXGPU_CUDA(cudaStreamSynchronize(s));  // host vectors die here
+            }
         }
         lap("upload band layouts");
         IPXGPU_TRY(dev_alloc(&c->t, (size_t)nloc));
@@ -1018,7 +1068,9 @@ int ipxgpu_get_tiling(ipxgpu_ctx* c, int64_t out[16]) {
         for (int j = 0; j < 8; j++) o[j] = 0;
         if (!ts[k]) continue;
         const BandPlan& P = ts[k]->plan;
-        o[0] = 1; o[1] = P.VB; o[2] = P.SB; o[3] = P.NVB; o[4] = P.NSB;
+        const Spill& sp = k == 0 ? c->spill1 : c->spill2;
+        o[0] = sp.nseg > 0 ? 2 : 1;  // 2: banded, with spilled (dense) segments swept generically
+        o[1] = P.VB; o[2] = P.SB; o[3] = P.NVB; o[4] = P.NSB;
         o[5] = P.K; o[6] = P.nparts; o[7] = P.nitems;
     }
     return IPXGPU_OK;
@@ -1501,13 +1553,16 @@ int ipxgpu_band_selftest(int64_t m, int64_t n, const int64_t* AIp, const int64_t
                                        : plan_band(&P, (int)n, (int)m, nnz, 148, ratio);
             if (!ok) continue;
             BandHost H;
-            const bool built = sweep == 0 ? band_build(P, cp.data(), ci.data(), AIx, &H)
-                                          : band_build(P, rp.data(), rj.data(), rx.data(), &H);
+            std::vector<int> spilled;  // dense segments: left out of the streams (sum 0)
+            const bool built =
+                sweep == 0 ? band_build(P, cp.data(), ci.data(), AIx, &H, kBandMaxRun, &spilled)
+                           : band_build(P, rp.data(), rj.data(), rx.data(), &H, kBandMaxRun, &spilled);
             if (!built) continue;
-            o[0] = 1.0;
+            o[0] = spilled.empty() ? 1.0 : 2.0;
             std::vector<double> got;
             band_emulate(P, H, sweep == 0 ? x : t_ref.data(), &got);
-            const std::vector<double>& ref = sweep == 0 ? t_ref : y_ref;
+            std::vector<double> ref = sweep == 0 ? t_ref : y_ref;
+            for (int sgm : spilled) ref[sgm] = 0.0;
             double e = 0.0;
             for (size_t i = 0; i < ref.size(); i++) e = std::max(e, std::fabs(got[i] - ref[i]));
             o[1] = e;
@@ -1546,6 +1601,10 @@ int ipxgpu_time_normal_apply(ipxgpu_ctx* c, int reps, int flush_l2, double out_m
             if (c->band1) {
                 BandArgs a1{c->xin, c->Wc, nullptr, nullptr, c->t, kApplyPlain, kSlotNone};
                 rc = launch_band(c, *c->band1, a1, kBandColScale, nullptr);
+                if (rc == IPXGPU_OK && c->spill1.nseg > 0) {
+                    OpColDotScaleSpill op{c->xin, c->Wc, c->t, c->spill1.map};
+                    rc = launch_sweep(c, op, c->spill1.tiles, c->spill1.A, nullptr);
+                }
             } else {
                 for (int k = 0; k < np && rc == IPXGPU_OK; k++) {
                     OpColDotScale op1{c->xin, c->Wc, c->t};
@@ -1556,6 +1615,11 @@ int ipxgpu_time_normal_apply(ipxgpu_ctx* c, int reps, int flush_l2, double out_m
             if (rc == IPXGPU_OK && c->band2) {
                 BandArgs a2{c->t, nullptr, c->Ws, c->xin, c->ybuf, kApplyPlain, kSlotNone};
                 rc = launch_band(c, *c->band2, a2, kBandRowFinal, nullptr);
+                if (rc == IPXGPU_OK && c->spill2.nseg > 0) {
+                    OpRowGatherSpill op{c->t, c->xin, c->ybuf, c->spill2.map, (int)c->m,
+                                        kApplyPlain, kSlotNone};
+                    rc = launch_sweep(c, op, c->spill2.tiles, c->spill2.A, nullptr);
+                }
             } else {
                 for (int k = 0; k < np && rc == IPXGPU_OK; k++) {
                     OpRowGather op2{c->t, c->xin, c->Ws, c->ybuf, (int)c->m, k == 0, k == np - 1,

@@ -159,6 +159,51 @@ struct OpRowGather {
     }
 };
 
+// Spilled segments of a banded sweep (context.cuh Spill). The banded kernel has written its
+// result for every segment with an empty sum for these; the generic kernel fills them in.
+// Sweep 1: t[map[k]] = W[map[k]] * sum.
+struct OpColDotScaleSpill {
+    static constexpr bool kReduce = false;
+    const double* x;
+    const double* W;
+    double* t;
+    const int* map;
+    __device__ __forceinline__ double prod(int i, double a) const {
+        return __dmul_rn(__ldg(x + i), a);
+    }
+    __device__ __forceinline__ double epilogue(int seg, double sum) const {
+        const int g = map[seg];
+        t[g] = W ? __dmul_rn(sum, W[g]) : sum;
+        return 0.0;
+    }
+    __device__ __forceinline__ void finalize(double, CrState*) const {}
+};
+
+// Sweep 2: y[map[k]] += sum; y[m] (= x'y so far) += x[map[k]] * sum, then the scalar step the
+// banded kernel left to this one.
+struct OpRowGatherSpill {
+    static constexpr bool kReduce = true;
+    const double* t;
+    const double* x;
+    double* y;  // m+1 entries
+    const int* map;
+    int m;
+    int mode, slot;
+    __device__ __forceinline__ double prod(int j, double a) const {
+        return __dmul_rn(__ldg(t + j), a);
+    }
+    __device__ __forceinline__ double epilogue(int seg, double sum) const {
+        const int g = map[seg];
+        y[g] = y[g] + sum;
+        return __dmul_rn(x[g], sum);
+    }
+    __device__ __forceinline__ void finalize(double total, CrState* st) const {
+        const double dot = y[m] + total;
+        y[m] = dot;
+        if (st) after_apply(st, mode, dot, slot);
+    }
+};
+
 // Diagonal build: d[i] = (first ? Ws[i] : d[i]) + sum_p W[col_p] a_p^2.
 struct OpRowDiag {
     static constexpr bool kReduce = false;

@@ -314,12 +314,21 @@ void ipxh_basis_fix_variable(void* self, ipxint j) {
     GetBasis(static_cast<Harness*>(self)).FixNonbasicVariable(j);
 }
 
+// The factors can only be exported from a fresh factorization; after updates
+// (crash basis repairs) refactorize first, as KKTSolverBasis::_Factorize does
+// (src/kkt_solver_basis.cc:59-63).
+static Basis& FreshBasis(Harness* h) {
+    Basis& B = GetBasis(h);
+    if (!B.FactorizationIsFresh()) B.Factorize();
+    return B;
+}
+
 // Returns nnz(L), nnz(U) of the fresh factorization (B[rowperm,colperm] =
 // (L+I)U, src/basis.h:109-118).
 void ipxh_basis_lu_sizes(void* self, ipxint* lnz, ipxint* unz) {
     Harness* h = static_cast<Harness*>(self);
     SparseMatrix L, U;
-    GetBasis(h).GetLuFactors(&L, &U, nullptr, nullptr);
+    FreshBasis(h).GetLuFactors(&L, &U, nullptr, nullptr);
     *lnz = L.entries();
     *unz = U.entries();
 }
@@ -329,7 +338,7 @@ void ipxh_basis_lu(void* self, ipxint* Lp, ipxint* Li, double* Lx, ipxint* Up,
     Harness* h = static_cast<Harness*>(self);
     const Int m = h->model.rows();
     SparseMatrix L, U;
-    GetBasis(h).GetLuFactors(&L, &U, rowperm, colperm);
+    FreshBasis(h).GetLuFactors(&L, &U, rowperm, colperm);
     std::memcpy(Lp, L.colptr(), (m + 1) * sizeof(ipxint));
     std::memcpy(Li, L.rowidx(), L.entries() * sizeof(ipxint));
     std::memcpy(Lx, L.values(), L.entries() * sizeof(double));
@@ -350,7 +359,7 @@ void ipxh_basis_solve_dense(void* self, const double* rhs, double* lhs,
 void ipxh_split_prepare(void* self, const double* colscale) {
     Harness* h = static_cast<Harness*>(self);
     if (!h->split) h->split.reset(new SplittedNormalMatrix(h->model));
-    h->split->Prepare(GetBasis(h), colscale);
+    h->split->Prepare(FreshBasis(h), colscale);
 }
 
 void ipxh_split_colperm(void* self, ipxint* colperm) {

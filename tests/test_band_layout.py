@@ -46,13 +46,43 @@ def test_forced_layout_is_exact_on_small_shapes(capi, shape):
 
 
 def test_long_segments_are_left_to_the_generic_sweep(capi):
-    """Transportation rows hold thousands of entries inside one band: sweep 2 must be
-    refused (the segmented generic kernel handles it), sweep 1 (2 entries per column) not."""
-    lp = lpgen.transportation_lp(20, 3000, 23)
+    """Transportation source rows hold thousands of entries inside one band: sweep 2 leaves
+    them out of the streams (planned == 2: the generic kernel sweeps those rows) and carries
+    the sink rows; sweep 1 (2 entries per column) takes everything."""
+    lp = lpgen.transportation_lp(400, 5000, 23)
     x = np.random.default_rng(3).standard_normal(lp.m)
-    r = capi.band_selftest(lp.m, lp.n, *_structural(lp), x, force=True)
-    assert r["sweep2"]["planned"] == 0.0
+    r = capi.band_selftest(lp.m, lp.n, *_structural(lp), x)
+    assert r["sweep2"]["planned"] == 2.0 and r["sweep2"]["err"] <= 1e-10, r
+    assert r["sweep2"]["pad"] < 0.25, r
     assert r["sweep1"]["planned"] == 1.0 and r["sweep1"]["err"] <= 1e-12
+
+
+def test_dense_row_and_column_are_spilled(capi):
+    """One dense row and one dense column in a well-spread matrix: both sweeps stay banded
+    and list one spilled segment each (planned == 2); the rest of the streams is exact."""
+    base = lpgen.random_sparse_lp(20000, 400000, 10, 33)
+    m, n = base.m, base.n
+    rng = np.random.default_rng(7)
+    # dense row m-1 in every other column (appended last keeps the rows sorted)
+    has = base.Ai.reshape(n, 10)[:, -1] == m - 1
+    add = (np.arange(n) % 2 == 0) & ~has
+    counts = 10 + add.astype(np.int64)
+    Ap = np.zeros(n + 2, np.int64)
+    Ap[1:n + 1] = np.cumsum(counts)
+    dense_col = np.arange(0, m, 3, dtype=np.int64)
+    Ap[n + 1] = Ap[n] + len(dense_col)
+    Ai = np.empty(Ap[n + 1], np.int64)
+    Ax = rng.uniform(0.5, 4.0, Ap[n + 1])
+    pos = Ap[:n, None] + np.arange(10)[None, :]
+    Ai[pos.reshape(-1)] = base.Ai
+    Ai[Ap[1:n + 1][add] - 1] = m - 1
+    Ai[Ap[n]:] = dense_col
+    x = rng.standard_normal(m)
+    r = capi.band_selftest(m, n + 1, Ap, Ai, Ax, x)
+    for sweep in ("sweep1", "sweep2"):
+        assert r[sweep]["planned"] == 2.0, r
+        assert r[sweep]["pad"] < 0.25, r
+    assert r["sweep1"]["err"] <= 1e-12 and r["sweep2"]["err"] <= 1e-10, r
 
 
 def test_small_problems_are_not_planned_without_force(capi):

@@ -326,6 +326,67 @@ def test_band_sweeps_auto(capi, oracle):
     ctx_gen.close()
 
 
+def _with_dense_row_and_column(lp, rng):
+    """Adds one dense column (every 3rd row) and one dense row (every 2nd column)."""
+    m, n = lp.m, lp.n
+    cols = [lp.Ai[lp.Ap[j]:lp.Ap[j + 1]] for j in range(n)]
+    dense_row = m - 1
+    Ap = np.zeros(n + 2, np.int64)
+    out_i, out_x = [], []
+    for j in range(n):
+        rows = cols[j]
+        if j % 2 == 0 and dense_row not in rows:
+            rows = np.append(rows, dense_row)
+        out_i.append(rows)
+        Ap[j + 1] = Ap[j] + len(rows)
+    dense_col = np.arange(0, m, 3, dtype=np.int64)
+    out_i.append(dense_col)
+    Ap[n + 1] = Ap[n] + len(dense_col)
+    Ai = np.concatenate(out_i)
+    Ax = rng.uniform(0.5, 4.0, len(Ai)) * rng.choice([-1.0, 1.0], len(Ai))
+    n2 = n + 1
+    return lpgen.LP(m, n2, Ap, Ai, Ax, np.zeros(m), b"=" * m, np.zeros(n2), np.zeros(n2),
+                    np.full(n2, np.inf), name="dense_row_and_column")
+
+
+def test_band_sweeps_spill_dense_segments(capi, oracle):
+    """A well-spread matrix with one dense row and one dense column: the banded sweeps keep
+    everything else and leave the two dense segments to the generic kernel (tiling 'enabled'
+    = 2); transportation rows (config 4 in small) take the same route in sweep 2."""
+    rng = np.random.default_rng(91)
+    base = lpgen.random_sparse_lp(20000, 400000, 10, 33)
+    cases = [_with_dense_row_and_column(base, rng), lpgen.transportation_lp(400, 5000, 34)]
+    for lp in cases:
+        m, n = lp.m, lp.n
+        AIp, AIi, AIx = lp.solver_form()
+        ctx = capi.Context(m, n, AIp, AIi, AIx)
+        tiling = ctx.tiling()
+        assert tiling["sweep2"]["enabled"] == 2, (lp.name, tiling)
+        if lp.name == "dense_row_and_column":
+            assert tiling["sweep1"]["enabled"] == 2, tiling
+        A = oracle.Csc(AIp, AIi, AIx)
+        x = rng.standard_normal(m)
+        for regime in ("ones", "wide", "null"):
+            W = None if regime == "null" else lpgen.weights(n + m, regime, 6)
+            ctx.normal_prepare(W)
+            y, dot = ctx.normal_apply(x)
+            y0, dot0 = oracle.normal_apply(m, n, A, W, x)
+            assert rel_err(y, y0) <= APPLY_TOL, (lp.name, regime)
+            assert abs(dot - dot0) <= APPLY_TOL * np.abs(x * y0).sum()
+            y2, dot2 = ctx.normal_apply(x)
+            assert np.array_equal(y, y2) and dot == dot2
+        W = lpgen.weights(n + m, "mid", 8)
+        ctx.normal_prepare(W)
+        ctx.diag_factorize(None, use_prepared=True)
+        d0 = oracle.diag_build(m, n, A, W)
+        rhs = rng.standard_normal(m)
+        zg, info = ctx.pcr_solve(rhs, 1e-30, None, 15)
+        zo, info0 = oracle.pcr_solve(oracle.normal_operator(m, n, A, W), m, d0, rhs, 1e-30, None, 15)
+        assert info["iter"] == info0["iter"] and info["errflag"] == info0["errflag"]
+        assert rel_err(zg, zo) <= 1e-8
+        ctx.close()
+
+
 def test_degenerate_shapes(capi, oracle):
     """No structural columns (a dualized LP without constraints, reference
     check/solver.cc:153-185) and no rows."""
