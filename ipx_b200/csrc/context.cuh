@@ -158,6 +158,9 @@ struct ipxgpu_ctx {
 
     // basis path
     ipxgpu::SplitOperator* split = nullptr;
+    unsigned* tri_flags = nullptr;  // m ready flags of the sync-free triangular solve
+    unsigned tri_gen = 0;           // flag value of the current solve
+    int tri_grid = 0;
 
     // banded shared-memory sweeps of the normal-matrix apply (may be null)
     ipxgpu::BandDev* band1 = nullptr;  // t = W .* (A'x): gather x, segments = columns

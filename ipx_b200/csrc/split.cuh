@@ -5,14 +5,27 @@
 // The reference solves L and U column-wise (scatter) and U', L' row-wise
 // (gather), all strictly sequentially. Here all four solves are in gather
 // form: every row i reads already-solved entries x[k], so the rows of one
-// dependency level are independent. Rows are bucketed by level on the host;
-// runs of narrow levels are executed by one CTA that steps through them with
-// __syncthreads(), wide levels by a full grid. Each row accumulates its
-// updates in exactly the order the reference applies them (rounded product,
-// then add/subtract), so the solves are bit-identical to the CPU loops.
+// dependency level are independent. Rows are bucketed by level on the host.
+// One persistent cooperative kernel per solve (tri_syncfree_kernel), no level barriers: the
+// rows are sorted by level and dealt to the grid's warps in that order; a warp owns a row,
+// loads 32 of its entries at a time (coalesced index/value loads), every lane waits for the
+// ready flag of the row its entry depends on, gathers x, and the 32 rounded products are
+// folded into the row's value one after the other with shuffles, i.e. in exactly the order
+// the reference applies them (rounded product, then add/subtract), so the solves are
+// bit-identical to the CPU loops. The finished row publishes x[i] and its flag (release).
+// Dependencies sit at earlier positions of the order and every warp walks its positions in
+// increasing order, so the earliest unfinished row can always proceed: no deadlock as long
+// as the grid is co-resident (cooperative launch). A dependency chain of length d costs d
+// flag round trips through L2 (~1 us each), not d kernel launches or grid barriers; rows
+// that merely follow each other in the order overlap.
+// (The first version gave a whole run of narrow levels to one CTA with one THREAD per row:
+// 1 s per apply on a 50,000-row basis whose factors hold 11 M entries and a dense trailing
+// block of 2000 rows - 25x slower than the CPU loops.)
 #pragma once
 
 #include <algorithm>
+#include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "context.cuh"
@@ -22,6 +35,7 @@ namespace ipxgpu {
 
 constexpr int kTriBlock = 1024;      // CTA of the merged-level kernel
 constexpr int kTriWideRows = 4096;   // levels at least this wide get a grid
+constexpr int kTriWarps = 16;        // warps per CTA of the sync-free kernel
 
 struct TriStep {
     int wide;        // 1: one level on a full grid; 0: levels [l0, l1) in one CTA
@@ -94,6 +108,98 @@ tri_levels_kernel(TriDev T, int l0, int l1, double* x, const CrState* st) {
         for (int r = rb + threadIdx.x; r < re; r += kTriBlock) tri_row(T, T.order[r], x);
         __syncthreads();
     }
+}
+
+__device__ __forceinline__ unsigned tri_flag(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// One row by one warp; the same arithmetic, in the same order, as tri_row. x is read and
+// written through L2 (other SMs solved the rows it depends on); flags[j] == gen says that
+// x[j] of this solve is final.
+//
+// The row is taken in batches of kTriBatch chunks of 32 entries: the index/value loads of
+// the whole batch go out together, then its flag loads, then (after one fence) the x loads
+// of every entry whose flag was up - three memory round trips per 256 entries instead of
+// three per 32, which is what a long row of a dense trailing block costs after the one
+// dependency it was really waiting for has resolved (in the L' solve the freshest
+// dependency comes FIRST in the reference's summation order). Entries whose flag was not up
+// yet are waited for when their chunk is due: all lanes look once, then only the first lane
+// still waiting polls (with a growing pause) - thousands of waiting warps must not saturate
+// the L2 slice that holds the flags.
+constexpr int kTriBatch = 8;
+
+__device__ __forceinline__ void tri_row_warp(const TriDev& T, int i, double* x, unsigned* flags,
+                                             unsigned gen, int lane) {
+    const int b = T.ptr[i], e = T.ptr[i + 1];
+    double v = __ldcg(x + i);
+    double d = 0.0;
+    for (int p0 = b; p0 < e; p0 += 32 * kTriBatch) {
+        int j[kTriBatch];
+        double a[kTriBatch], xv[kTriBatch];
+        bool ready[kTriBatch];
+#pragma unroll
+        for (int u = 0; u < kTriBatch; u++) {
+            const int p = p0 + 32 * u + lane;
+            const bool active = p < e;
+            j[u] = active ? __ldg(T.idx + p) : -1;
+            a[u] = active ? __ldg(T.val + p) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < kTriBatch; u++) ready[u] = j[u] < 0 || tri_flag(flags + j[u]) == gen;
+        __threadfence();  // acquire: x[j] is read after its flag
+#pragma unroll
+        for (int u = 0; u < kTriBatch; u++) xv[u] = (ready[u] && j[u] >= 0) ? __ldcg(x + j[u]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < kTriBatch; u++) {
+            const int cnt = min(32, e - (p0 + 32 * u));
+            if (cnt <= 0) break;  // uniform
+            if (__ballot_sync(0xffffffffu, !ready[u]) != 0u) {
+                bool ok = ready[u];
+                unsigned pause = 0;
+                for (;;) {
+                    if (!ok) ok = tri_flag(flags + j[u]) == gen;
+                    const unsigned pending = __ballot_sync(0xffffffffu, !ok);
+                    if (pending == 0u) break;
+                    if (lane == __ffs(pending) - 1) {
+                        while (tri_flag(flags + j[u]) != gen) {
+                            if (pause) __nanosleep(pause);
+                            pause = min(2 * pause + 32u, 1024u);
+                        }
+                        ok = true;
+                    }
+                    __syncwarp();
+                }
+                __threadfence();
+                if (!ready[u]) xv[u] = __ldcg(x + j[u]);
+            }
+            const double prod = __dmul_rn(a[u], xv[u]);
+            if (T.subtract_seq) {
+                for (int k = 0; k < cnt; k++) v = v - __shfl_sync(0xffffffffu, prod, k);
+            } else {
+                for (int k = 0; k < cnt; k++) d = d + __shfl_sync(0xffffffffu, prod, k);
+            }
+        }
+    }
+    if (!T.subtract_seq) v = v - d;
+    if (T.diag) v = v / __ldg(T.diag + i);
+    if (lane == 0) {
+        __stcg(x + i, v);
+        __threadfence();
+        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + i), "r"(gen) : "memory");
+    }
+}
+
+// Whole solve in one cooperative launch (the grid must be co-resident, see above).
+__global__ void __launch_bounds__(kTriWarps * 32, 2)
+tri_syncfree_kernel(TriDev T, double* x, unsigned* flags, unsigned gen, const CrState* st) {
+    if (st && st->done) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gwarp = blockIdx.x * kTriWarps + warp;
+    const int nwarps = gridDim.x * kTriWarps;
+    for (int r = gwarp; r < T.dim; r += nwarps) tri_row_warp(T, T.order[r], x, flags, gen, lane);
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -231,6 +337,38 @@ static int build_tri(ipxgpu_ctx* c, TriSystem* T, int dim, const std::vector<int
 }
 
 static int launch_tri(ipxgpu_ctx* c, const TriSystem& T, double* x, const CrState* st) {
+    static const bool legacy = [] {
+        const char* env = std::getenv("IPXGPU_TRI");
+        return env && std::string(env) == "levels";
+    }();
+    if (!legacy) {
+        if (T.d.dim == 0) return IPXGPU_OK;
+        if (c->tri_grid == 0) {
+            int per_sm = 0;
+            IPXGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tri_syncfree_kernel,
+                                                                     kTriWarps * 32, 0));
+            if (per_sm < 1) return fail(IPXGPU_ERR_STATE, "triangular solve kernel does not fit an SM");
+            c->tri_grid = c->num_sms * std::min(per_sm, 4);
+            IPXGPU_TRY(dev_alloc(&c->tri_flags, (size_t)c->m));
+            IPXGPU_CUDA(cudaMemsetAsync(c->tri_flags, 0, sizeof(unsigned) * (size_t)c->m, c->stream));
+            c->tri_gen = 0;
+        }
+        if (++c->tri_gen == 0) {  // generation wrapped: start over with clean flags
+            IPXGPU_CUDA(cudaMemsetAsync(c->tri_flags, 0, sizeof(unsigned) * (size_t)c->m, c->stream));
+            c->tri_gen = 1;
+        }
+        const int grid = std::max(1, std::min(c->tri_grid, (T.d.dim + kTriWarps - 1) / kTriWarps));
+        TriDev d = T.d;
+        double* xp = x;
+        unsigned* flags = c->tri_flags;
+        unsigned gen = c->tri_gen;
+        const CrState* stp = st;
+        void* args[] = {&d, &xp, &flags, &gen, &stp};
+        IPXGPU_CUDA(cudaLaunchCooperativeKernel((void*)tri_syncfree_kernel, dim3(grid),
+                                                dim3(kTriWarps * 32), args, 0, c->stream));
+        c->launches++;
+        return IPXGPU_OK;
+    }
     for (const TriStep& sp : T.steps) {
         if (sp.wide) {
             const int rows = sp.r1 - sp.r0;
