@@ -111,7 +111,12 @@ static int launch_band(ipxgpu_ctx* c, const BandDev& T, const BandArgs& A, int m
     } else {
         band_sweep_kernel<kBandWarps, kBandDepth>
             <<<P.nitems, threads, P.smem, c->stream>>>(T, A, kBandPartial, c->red, st);
-        band_combine_kernel<<<grid_for(c, P.S), kBlock, 0, c->stream>>>(T, A, mode, c->red, st);
+        if (P.nparts >= kBandWideParts) {
+            const int grid = std::max(1, std::min((P.S + 31) / 32, c->num_sms * 8));
+            band_combine_wide_kernel<<<grid, kBlock, 0, c->stream>>>(T, A, mode, c->red, st);
+        } else {
+            band_combine_kernel<<<grid_for(c, P.S), kBlock, 0, c->stream>>>(T, A, mode, c->red, st);
+        }
         c->launches += 2;
     }
     IPXGPU_CUDA(cudaGetLastError());

@@ -436,6 +436,59 @@ band_combine_kernel(BandDev T, BandArgs A, int mode, Reduce red, CrState* st) {
     }
 }
 
+// The same for many parts (>= kBandWideParts, e.g. 136 parts x 7000 rows of a transportation
+// LP): a CTA takes 32 segments, its 8 warps sum every 8th part each (coalesced rows of the
+// partials, several loads in flight) and warp 0 adds the 8 sums in warp order - a fixed
+// order, so the result is deterministic. (band_combine_kernel walks the parts one thread per
+// segment: 59 us for 7.7 MB there, latency bound on 28 CTAs.)
+constexpr int kBandWideParts = 16;
+
+__global__ void __launch_bounds__(kBlock)
+band_combine_wide_kernel(BandDev T, BandArgs A, int mode, Reduce red, CrState* st) {
+    static_assert(kBlock == 256, "8 warps of 32 segments");
+    __shared__ double s_part[8][32];
+    __shared__ double s_red[kWarps];
+    __shared__ int s_flag;
+    if (st != nullptr && st->done) return;
+    const int S = T.plan.S, nparts = T.plan.nparts;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double dot = 0.0;
+    for (int g0 = blockIdx.x * 32; g0 < S; g0 += gridDim.x * 32) {
+        const int g = g0 + lane;
+        double acc = 0.0;
+        if (g < S) {
+#pragma unroll 4
+            for (int p = warp; p < nparts; p += 8) acc += __ldcg(T.partials + (size_t)p * S + g);
+        }
+        s_part[warp][lane] = acc;
+        __syncthreads();
+        if (warp == 0 && g < S) {
+            double tot = 0.0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) tot += s_part[w][lane];
+            if (mode == kBandColScale) {
+                A.out[g] = A.W ? __dmul_rn(tot, A.W[g]) : tot;
+            } else {
+                const double xv = A.x[g];
+                const double yv = (A.Ws ? __dmul_rn(xv, A.Ws[g]) : 0.0) + tot;
+                A.out[g] = yv;
+                dot += __dmul_rn(xv, yv);
+            }
+        }
+        __syncthreads();
+    }
+    if (mode == kBandRowFinal) {
+        const double mine = block_sum(dot, s_red);
+        double ts, ts2, tm;
+        if (grid_reduce(red, mine, 0.0, 0.0, s_red, &s_flag, &ts, &ts2, &tm) &&
+            threadIdx.x == 0) {
+            A.out[S] = ts;
+            if (st && !(A.apply_mode == kApplyPlain && A.slot == kSlotNone))
+                after_apply(st, A.apply_mode, ts, A.slot);
+        }
+    }
+}
+
 // ---- host side ----
 
 inline size_t band_smem_bytes(const BandPlan& P) {
