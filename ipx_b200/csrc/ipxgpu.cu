@@ -30,8 +30,11 @@ struct HostTiles {
     std::vector<int> long_first;  // prefix over chunks, size num_long+1
 };
 
+// `long_chunk`: entries per CTA for segments longer than a tile (the kernel's single-segment
+// path takes any length; the spilled dense segments use larger chunks than kTileNnz).
 template <class P>
-static HostTiles build_tiles(const P* ptr, int seg_begin, int seg_end, long long base) {
+static HostTiles build_tiles(const P* ptr, int seg_begin, int seg_end, long long base,
+                             int long_chunk = kTileNnz) {
     HostTiles out;
     out.long_first.push_back(0);
     int s = seg_begin;
@@ -39,14 +42,14 @@ static HostTiles build_tiles(const P* ptr, int seg_begin, int seg_end, long long
         const long long p0 = ptr[s] - base;
         const long long len = ptr[s + 1] - ptr[s];
         if (len > kTileNnz) {
-            const int nch = (int)((len + kTileNnz - 1) / kTileNnz);
+            const int nch = (int)((len + long_chunk - 1) / long_chunk);
             const int long_id = (int)out.long_first.size() - 1;
             for (int c = 0; c < nch; c++) {
                 Tile t;
                 t.seg0 = s;
                 t.nseg = 1;
-                t.p0 = (int)(p0 + (long long)c * kTileNnz);
-                t.p1 = (int)std::min<long long>(p0 + len, p0 + (long long)(c + 1) * kTileNnz);
+                t.p0 = (int)(p0 + (long long)c * long_chunk);
+                t.p1 = (int)std::min<long long>(p0 + len, p0 + (long long)(c + 1) * long_chunk);
                 t.long_id = long_id;
                 t.chunk = c;
                 out.tiles.push_back(t);
@@ -1020,7 +1023,7 @@ int ipxgpu_create(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp, co
                 IPXGPU_TRY(upload(&sp.A.idx, sidx, s));
                 IPXGPU_TRY(upload(&sp.A.val, sval, s));
                 IPXGPU_TRY(upload(&sp.map, job.spilled, s));
-                HostTiles st = build_tiles(sptr.data(), 0, ns, 0);
+                HostTiles st = build_tiles(sptr.data(), 0, ns, 0, 8 * kTileNnz);
                 IPXGPU_TRY(upload_tiles(&sp.tiles, st, s));
                 max_grid = std::max(max_grid, sp.tiles.ntiles);
                 IPXGPU_CUDA(cudaStreamSynchronize(s));  // host vectors die here

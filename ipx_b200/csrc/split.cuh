@@ -35,7 +35,7 @@ namespace ipxgpu {
 
 constexpr int kTriBlock = 1024;      // CTA of the merged-level kernel
 constexpr int kTriWideRows = 4096;   // levels at least this wide get a grid
-constexpr int kTriWarps = 16;        // warps per CTA of the sync-free kernel
+constexpr int kTriWarps = 12;        // warps per CTA of the sync-free kernel (16 KB of stash each)
 
 struct TriStep {
     int wide;        // 1: one level on a full grid; 0: levels [l0, l1) in one CTA
@@ -48,6 +48,8 @@ struct TriDev {
     int dim = 0;
     int subtract_seq = 0;  // 1: v -= a*x per entry (L, U column sweeps of the
                            // reference); 0: v = x[i] - sum (U', L' row sweeps)
+    int reverse = 0;       // 1: a row's entries resolve back to front (L': the reference sums
+                           // a column of L from the diagonal downwards, the solve runs upwards)
     int* ptr = nullptr;    // [dim+1] off-diagonal entries of row i
     int* idx = nullptr;
     double* val = nullptr;
@@ -120,66 +122,115 @@ __device__ __forceinline__ unsigned tri_flag(const unsigned* p) {
 // written through L2 (other SMs solved the rows it depends on); flags[j] == gen says that
 // x[j] of this solve is final.
 //
-// The row is taken in batches of kTriBatch chunks of 32 entries: the index/value loads of
-// the whole batch go out together, then its flag loads, then (after one fence) the x loads
-// of every entry whose flag was up - three memory round trips per 256 entries instead of
-// three per 32, which is what a long row of a dense trailing block costs after the one
-// dependency it was really waiting for has resolved (in the L' solve the freshest
-// dependency comes FIRST in the reference's summation order). Entries whose flag was not up
-// yet are waited for when their chunk is due: all lanes look once, then only the first lane
-// still waiting polls (with a growing pause) - thousands of waiting warps must not saturate
-// the L2 slice that holds the flags.
+// Two phases per row (per piece of kTriStash entries for longer rows):
+//  A. never blocks: in batches of kTriBatch chunks of 32 entries the index/value loads go out
+//     together, then the flag loads, then (after one fence) the x loads of every entry whose
+//     flag was up - three memory round trips per 256 entries. Each lane parks its rounded
+//     products in its own shared-memory slots and remembers which of its entries were not
+//     ready.
+//  B. in order: chunk by chunk the 32 products are folded into the row value with shuffles.
+//     A chunk with entries that were not ready waits for them first: all lanes look once, then
+//     only the first lane still waiting polls (with a growing pause), so thousands of waiting
+//     warps do not saturate the L2 slice that holds the flags.
+// So whatever a row can prepare is prepared while it waits for its last dependency, wherever
+// that sits in the summation order: in the L' solve the reference sums a row starting with
+// the entry next to the diagonal, i.e. the dependency that resolves LAST, and without phase A
+// a 1000-entry row of a dense trailing block paid all its memory round trips after that.
 constexpr int kTriBatch = 8;
+constexpr int kTriStash = 2048;  // parked products per warp (16 KB)
 
 __device__ __forceinline__ void tri_row_warp(const TriDev& T, int i, double* x, unsigned* flags,
-                                             unsigned gen, int lane) {
+                                             unsigned gen, int lane, double* stash) {
     const int b = T.ptr[i], e = T.ptr[i + 1];
     double v = __ldcg(x + i);
     double d = 0.0;
-    for (int p0 = b; p0 < e; p0 += 32 * kTriBatch) {
-        int j[kTriBatch];
-        double a[kTriBatch], xv[kTriBatch];
-        bool ready[kTriBatch];
+    for (int q0 = b; q0 < e; q0 += kTriStash) {
+        const int qe = min(e, q0 + kTriStash);
+        unsigned long long mypend = 0ull;  // bit c: my entry of chunk c was not ready in phase A
+        for (int p0 = q0; p0 < qe; p0 += 32 * kTriBatch) {
+            int j[kTriBatch];
+            double a[kTriBatch];
+            bool ready[kTriBatch];
 #pragma unroll
-        for (int u = 0; u < kTriBatch; u++) {
-            const int p = p0 + 32 * u + lane;
-            const bool active = p < e;
-            j[u] = active ? __ldg(T.idx + p) : -1;
-            a[u] = active ? __ldg(T.val + p) : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < kTriBatch; u++) ready[u] = j[u] < 0 || tri_flag(flags + j[u]) == gen;
-        __threadfence();  // acquire: x[j] is read after its flag
-#pragma unroll
-        for (int u = 0; u < kTriBatch; u++) xv[u] = (ready[u] && j[u] >= 0) ? __ldcg(x + j[u]) : 0.0;
-#pragma unroll
-        for (int u = 0; u < kTriBatch; u++) {
-            const int cnt = min(32, e - (p0 + 32 * u));
-            if (cnt <= 0) break;  // uniform
-            if (__ballot_sync(0xffffffffu, !ready[u]) != 0u) {
-                bool ok = ready[u];
-                unsigned pause = 0;
-                for (;;) {
-                    if (!ok) ok = tri_flag(flags + j[u]) == gen;
-                    const unsigned pending = __ballot_sync(0xffffffffu, !ok);
-                    if (pending == 0u) break;
-                    if (lane == __ffs(pending) - 1) {
-                        while (tri_flag(flags + j[u]) != gen) {
-                            if (pause) __nanosleep(pause);
-                            pause = min(2 * pause + 32u, 1024u);
-                        }
-                        ok = true;
-                    }
-                    __syncwarp();
-                }
-                __threadfence();
-                if (!ready[u]) xv[u] = __ldcg(x + j[u]);
+            for (int u = 0; u < kTriBatch; u++) {
+                const int p = p0 + 32 * u + lane;
+                const bool active = p < qe;
+                j[u] = active ? __ldg(T.idx + p) : -1;
+                a[u] = active ? __ldg(T.val + p) : 0.0;
             }
-            const double prod = __dmul_rn(a[u], xv[u]);
+#pragma unroll
+            for (int u = 0; u < kTriBatch; u++)
+                ready[u] = j[u] < 0 || tri_flag(flags + j[u]) == gen;
+            __threadfence();  // acquire: x[j] is read after its flag
+            const int c0 = (p0 - q0) >> 5;
+#pragma unroll
+            for (int u = 0; u < kTriBatch; u++) {
+                if (p0 + 32 * u >= qe) break;  // uniform
+                double prod = 0.0;
+                if (j[u] >= 0 && ready[u]) prod = __dmul_rn(a[u], __ldcg(x + j[u]));
+                stash[(c0 + u) * 32 + lane] = prod;
+                if (!ready[u]) mypend |= 1ull << (c0 + u);
+            }
+        }
+        const int nchunks = (qe - q0 + 31) >> 5;
+        // Waits for the entries of chunk c that were not ready in phase A and returns this
+        // lane's product of the chunk.
+        auto resolve = [&](int c, double prod) -> double {
+            const bool mine = (mypend >> c) & 1ull;
+            if (__ballot_sync(0xffffffffu, mine) == 0u) return prod;
+            int jj = 0;
+            double aa = 0.0;
+            if (mine) {
+                jj = __ldg(T.idx + q0 + 32 * c + lane);
+                aa = __ldg(T.val + q0 + 32 * c + lane);
+            }
+            bool ok = !mine;
+            unsigned pause = 0;
+            for (;;) {
+                if (!ok) ok = tri_flag(flags + jj) == gen;
+                const unsigned pending = __ballot_sync(0xffffffffu, !ok);
+                if (pending == 0u) break;
+                if (lane == __ffs(pending) - 1) {
+                    while (tri_flag(flags + jj) != gen) {
+                        if (pause) __nanosleep(pause);
+                        pause = min(2 * pause + 32u, 256u);
+                    }
+                    ok = true;
+                }
+                __syncwarp();
+            }
+            __threadfence();
+            if (mine) prod = __dmul_rn(aa, __ldcg(x + jj));
+            return prod;
+        };
+        if (T.reverse) {
+            // The dependencies of the LAST chunk resolve first (see above): wait for the
+            // chunks back to front and park the products, then sum front to back.
+            for (int c = nchunks - 1; c >= 0; c--) {
+                if (__ballot_sync(0xffffffffu, (mypend >> c) & 1ull) == 0u) continue;
+                stash[c * 32 + lane] = resolve(c, stash[c * 32 + lane]);
+            }
+            mypend = 0ull;
+        }
+        for (int c = 0; c < nchunks; c++) {
+            const int cnt = min(32, qe - (q0 + 32 * c));
+            const double prod = resolve(c, stash[c * 32 + lane]);
+            // Full chunks unrolled: the 32 shuffles go out back to back and only the chain of
+            // additions stays serial (a rolled loop pays shuffle latency + add per entry).
             if (T.subtract_seq) {
-                for (int k = 0; k < cnt; k++) v = v - __shfl_sync(0xffffffffu, prod, k);
+                if (cnt == 32) {
+#pragma unroll
+                    for (int k = 0; k < 32; k++) v = v - __shfl_sync(0xffffffffu, prod, k);
+                } else {
+                    for (int k = 0; k < cnt; k++) v = v - __shfl_sync(0xffffffffu, prod, k);
+                }
             } else {
-                for (int k = 0; k < cnt; k++) d = d + __shfl_sync(0xffffffffu, prod, k);
+                if (cnt == 32) {
+#pragma unroll
+                    for (int k = 0; k < 32; k++) d = d + __shfl_sync(0xffffffffu, prod, k);
+                } else {
+                    for (int k = 0; k < cnt; k++) d = d + __shfl_sync(0xffffffffu, prod, k);
+                }
             }
         }
     }
@@ -187,19 +238,22 @@ __device__ __forceinline__ void tri_row_warp(const TriDev& T, int i, double* x, 
     if (T.diag) v = v / __ldg(T.diag + i);
     if (lane == 0) {
         __stcg(x + i, v);
-        __threadfence();
+        // release: x[i] (same thread) is visible before the flag
         asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + i), "r"(gen) : "memory");
     }
 }
 
 // Whole solve in one cooperative launch (the grid must be co-resident, see above).
-__global__ void __launch_bounds__(kTriWarps * 32, 2)
+__global__ void __launch_bounds__(kTriWarps * 32, 1)
 tri_syncfree_kernel(TriDev T, double* x, unsigned* flags, unsigned gen, const CrState* st) {
+    extern __shared__ __align__(16) double tri_stash[];  // kTriWarps * kTriStash
     if (st && st->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gwarp = blockIdx.x * kTriWarps + warp;
     const int nwarps = gridDim.x * kTriWarps;
-    for (int r = gwarp; r < T.dim; r += nwarps) tri_row_warp(T, T.order[r], x, flags, gen, lane);
+    double* stash = tri_stash + (size_t)warp * kTriStash;
+    for (int r = gwarp; r < T.dim; r += nwarps)
+        tri_row_warp(T, T.order[r], x, flags, gen, lane, stash);
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -344,11 +398,14 @@ static int launch_tri(ipxgpu_ctx* c, const TriSystem& T, double* x, const CrStat
     if (!legacy) {
         if (T.d.dim == 0) return IPXGPU_OK;
         if (c->tri_grid == 0) {
+            const size_t smem = (size_t)kTriWarps * kTriStash * sizeof(double);
+            IPXGPU_CUDA(cudaFuncSetAttribute(tri_syncfree_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int per_sm = 0;
             IPXGPU_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tri_syncfree_kernel,
-                                                                     kTriWarps * 32, 0));
+                                                                     kTriWarps * 32, smem));
             if (per_sm < 1) return fail(IPXGPU_ERR_STATE, "triangular solve kernel does not fit an SM");
-            c->tri_grid = c->num_sms * std::min(per_sm, 4);
+            c->tri_grid = c->num_sms * per_sm;
             IPXGPU_TRY(dev_alloc(&c->tri_flags, (size_t)c->m));
             IPXGPU_CUDA(cudaMemsetAsync(c->tri_flags, 0, sizeof(unsigned) * (size_t)c->m, c->stream));
             c->tri_gen = 0;
@@ -365,7 +422,9 @@ static int launch_tri(ipxgpu_ctx* c, const TriSystem& T, double* x, const CrStat
         const CrState* stp = st;
         void* args[] = {&d, &xp, &flags, &gen, &stp};
         IPXGPU_CUDA(cudaLaunchCooperativeKernel((void*)tri_syncfree_kernel, dim3(grid),
-                                                dim3(kTriWarps * 32), args, 0, c->stream));
+                                                dim3(kTriWarps * 32), args,
+                                                (size_t)kTriWarps * kTriStash * sizeof(double),
+                                                c->stream));
         c->launches++;
         return IPXGPU_OK;
     }
