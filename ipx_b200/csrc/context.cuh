@@ -158,8 +158,8 @@ struct ipxgpu_ctx {
 
     // basis path
     ipxgpu::SplitOperator* split = nullptr;
-    unsigned* tri_flags = nullptr;  // m ready flags of the sync-free triangular solve
-    unsigned tri_gen = 0;           // flag value of the current solve
+    ulonglong2* tri_ll = nullptr;   // m records {generation | x halves} of the sync-free solves
+    unsigned tri_gen = 0;           // generation of the current solve
     int tri_grid = 0;
 
     // banded shared-memory sweeps of the normal-matrix apply (may be null)

@@ -697,7 +697,7 @@ void ipxgpu_destroy(ipxgpu_ctx* c) {
     if (c->xchg) cudaFree(c->xchg);
     dev_free(c->peer_dev);
     dev_free(c->fused_bar);
-    dev_free(c->tri_flags);
+    dev_free(c->tri_ll);
     dev_free(c->fused_tickets);
     dev_free(c->fused_red);
     if (c->band1) { free_band(c->band1); delete c->band1; }

@@ -112,10 +112,26 @@ tri_levels_kernel(TriDev T, int l0, int l1, double* x, const CrState* st) {
     }
 }
 
-__device__ __forceinline__ unsigned tri_flag(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+// Solved entries travel as 16-byte records of two self-validating 64-bit words
+// {generation : 32 | low half of x}, {generation : 32 | high half of x} (the layout of NCCL's LL
+// protocol): a 64-bit word is read and written atomically, so a reader that finds this solve's
+// generation in both words holds the final x[j] - no separate flag, no fence on either side,
+// one L2 round trip per dependency instead of two.
+__device__ __forceinline__ bool tri_ll_load(const ulonglong2* p, unsigned gen, double* val) {
+    unsigned long long w0, w1;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];"
+                 : "=l"(w0), "=l"(w1)
+                 : "l"(p)
+                 : "memory");
+    *val = __longlong_as_double((long long)(((w1 & 0xffffffffull) << 32) | (w0 & 0xffffffffull)));
+    return (unsigned)(w0 >> 32) == gen && (unsigned)(w1 >> 32) == gen;
+}
+__device__ __forceinline__ void tri_ll_store(ulonglong2* p, unsigned gen, double v) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long w0 = ((unsigned long long)gen << 32) | (bits & 0xffffffffull);
+    const unsigned long long w1 = ((unsigned long long)gen << 32) | (bits >> 32);
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1)
+                 : "memory");
 }
 
 // One row by one warp; the same arithmetic, in the same order, as tri_row. x is read and
@@ -139,7 +155,7 @@ __device__ __forceinline__ unsigned tri_flag(const unsigned* p) {
 constexpr int kTriBatch = 8;
 constexpr int kTriStash = 2048;  // parked products per warp (16 KB)
 
-__device__ __forceinline__ void tri_row_warp(const TriDev& T, int i, double* x, unsigned* flags,
+__device__ __forceinline__ void tri_row_warp(const TriDev& T, int i, double* x, ulonglong2* ll,
                                              unsigned gen, int lane, double* stash) {
     const int b = T.ptr[i], e = T.ptr[i + 1];
     double v = __ldcg(x + i);
@@ -149,7 +165,7 @@ __device__ __forceinline__ void tri_row_warp(const TriDev& T, int i, double* x, 
         unsigned long long mypend = 0ull;  // bit c: my entry of chunk c was not ready in phase A
         for (int p0 = q0; p0 < qe; p0 += 32 * kTriBatch) {
             int j[kTriBatch];
-            double a[kTriBatch];
+            double a[kTriBatch], xv[kTriBatch];
             bool ready[kTriBatch];
 #pragma unroll
             for (int u = 0; u < kTriBatch; u++) {
@@ -159,16 +175,15 @@ __device__ __forceinline__ void tri_row_warp(const TriDev& T, int i, double* x, 
                 a[u] = active ? __ldg(T.val + p) : 0.0;
             }
 #pragma unroll
-            for (int u = 0; u < kTriBatch; u++)
-                ready[u] = j[u] < 0 || tri_flag(flags + j[u]) == gen;
-            __threadfence();  // acquire: x[j] is read after its flag
+            for (int u = 0; u < kTriBatch; u++) {
+                xv[u] = 0.0;
+                ready[u] = j[u] < 0 || tri_ll_load(ll + j[u], gen, &xv[u]);
+            }
             const int c0 = (p0 - q0) >> 5;
 #pragma unroll
             for (int u = 0; u < kTriBatch; u++) {
                 if (p0 + 32 * u >= qe) break;  // uniform
-                double prod = 0.0;
-                if (j[u] >= 0 && ready[u]) prod = __dmul_rn(a[u], __ldcg(x + j[u]));
-                stash[(c0 + u) * 32 + lane] = prod;
+                stash[(c0 + u) * 32 + lane] = (j[u] >= 0 && ready[u]) ? __dmul_rn(a[u], xv[u]) : 0.0;
                 if (!ready[u]) mypend |= 1ull << (c0 + u);
             }
         }
@@ -185,13 +200,14 @@ __device__ __forceinline__ void tri_row_warp(const TriDev& T, int i, double* x, 
                 aa = __ldg(T.val + q0 + 32 * c + lane);
             }
             bool ok = !mine;
+            double xj = 0.0;
             unsigned pause = 0;
             for (;;) {
-                if (!ok) ok = tri_flag(flags + jj) == gen;
+                if (!ok) ok = tri_ll_load(ll + jj, gen, &xj);
                 const unsigned pending = __ballot_sync(0xffffffffu, !ok);
                 if (pending == 0u) break;
                 if (lane == __ffs(pending) - 1) {
-                    while (tri_flag(flags + jj) != gen) {
+                    while (!tri_ll_load(ll + jj, gen, &xj)) {
                         if (pause) __nanosleep(pause);
                         pause = min(2 * pause + 32u, 256u);
                     }
@@ -199,8 +215,7 @@ __device__ __forceinline__ void tri_row_warp(const TriDev& T, int i, double* x, 
                 }
                 __syncwarp();
             }
-            __threadfence();
-            if (mine) prod = __dmul_rn(aa, __ldcg(x + jj));
+            if (mine) prod = __dmul_rn(aa, xj);
             return prod;
         };
         if (T.reverse) {
@@ -237,15 +252,14 @@ __device__ __forceinline__ void tri_row_warp(const TriDev& T, int i, double* x, 
     if (!T.subtract_seq) v = v - d;
     if (T.diag) v = v / __ldg(T.diag + i);
     if (lane == 0) {
-        __stcg(x + i, v);
-        // release: x[i] (same thread) is visible before the flag
-        asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flags + i), "r"(gen) : "memory");
+        tri_ll_store(ll + i, gen, v);  // what the dependent rows read
+        x[i] = v;                      // the result
     }
 }
 
 // Whole solve in one cooperative launch (the grid must be co-resident, see above).
 __global__ void __launch_bounds__(kTriWarps * 32, 1)
-tri_syncfree_kernel(TriDev T, double* x, unsigned* flags, unsigned gen, const CrState* st) {
+tri_syncfree_kernel(TriDev T, double* x, ulonglong2* ll, unsigned gen, const CrState* st) {
     extern __shared__ __align__(16) double tri_stash[];  // kTriWarps * kTriStash
     if (st && st->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -253,7 +267,7 @@ tri_syncfree_kernel(TriDev T, double* x, unsigned* flags, unsigned gen, const Cr
     const int nwarps = gridDim.x * kTriWarps;
     double* stash = tri_stash + (size_t)warp * kTriStash;
     for (int r = gwarp; r < T.dim; r += nwarps)
-        tri_row_warp(T, T.order[r], x, flags, gen, lane, stash);
+        tri_row_warp(T, T.order[r], x, ll, gen, lane, stash);
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -406,21 +420,21 @@ static int launch_tri(ipxgpu_ctx* c, const TriSystem& T, double* x, const CrStat
                                                                      kTriWarps * 32, smem));
             if (per_sm < 1) return fail(IPXGPU_ERR_STATE, "triangular solve kernel does not fit an SM");
             c->tri_grid = c->num_sms * per_sm;
-            IPXGPU_TRY(dev_alloc(&c->tri_flags, (size_t)c->m));
-            IPXGPU_CUDA(cudaMemsetAsync(c->tri_flags, 0, sizeof(unsigned) * (size_t)c->m, c->stream));
+            IPXGPU_TRY(dev_alloc(&c->tri_ll, (size_t)c->m));
+            IPXGPU_CUDA(cudaMemsetAsync(c->tri_ll, 0, sizeof(ulonglong2) * (size_t)c->m, c->stream));
             c->tri_gen = 0;
         }
         if (++c->tri_gen == 0) {  // generation wrapped: start over with clean flags
-            IPXGPU_CUDA(cudaMemsetAsync(c->tri_flags, 0, sizeof(unsigned) * (size_t)c->m, c->stream));
+            IPXGPU_CUDA(cudaMemsetAsync(c->tri_ll, 0, sizeof(ulonglong2) * (size_t)c->m, c->stream));
             c->tri_gen = 1;
         }
         const int grid = std::max(1, std::min(c->tri_grid, (T.d.dim + kTriWarps - 1) / kTriWarps));
         TriDev d = T.d;
         double* xp = x;
-        unsigned* flags = c->tri_flags;
+        ulonglong2* ll = c->tri_ll;
         unsigned gen = c->tri_gen;
         const CrState* stp = st;
-        void* args[] = {&d, &xp, &flags, &gen, &stp};
+        void* args[] = {&d, &xp, &ll, &gen, &stp};
         IPXGPU_CUDA(cudaLaunchCooperativeKernel((void*)tri_syncfree_kernel, dim3(grid),
                                                 dim3(kTriWarps * 32), args,
                                                 (size_t)kTriWarps * kTriStash * sizeof(double),
