@@ -179,7 +179,7 @@ def run_basis_checks(name, lp, reflib, gpulib, log=print):
         t0 = time.time()
         _, parts = mdl.split_apply_timed(x, reps)
         out[f"split_apply_{key}_ms"] = 1e3 * (time.time() - t0) / reps
-        out[f"split_apply_{key}_parts_ms"] = {k: 1e3 * v / reps for k, v in parts.items()}
+        out[f"split_apply_{key}_parts_ms"] = {k: 1e3 * v for k, v in parts.items()}
     rhs = rng.standard_normal(m)
     t0 = time.time()
     z0, i0 = ref.cr_solve_split(rhs, 1e-8, 200)
@@ -202,11 +202,13 @@ def run_basis_checks(name, lp, reflib, gpulib, log=print):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("configs", nargs="*", default=["C2"])
+    ap.add_argument("configs", nargs="*", default=[])
     ap.add_argument("--basis", nargs="*", default=[])
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
+    if not args.configs and not args.basis:
+        args.configs = ["C2"]
     from ipx_b200 import capi, ipxlib
     from oracle import pyoracle
     capi.load()
