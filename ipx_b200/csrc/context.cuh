@@ -160,6 +160,7 @@ struct ipxgpu_ctx {
     ipxgpu::SplitOperator* split = nullptr;
     ulonglong2* tri_ll = nullptr;   // m records {generation | x halves} of the sync-free solves
     unsigned tri_gen = 0;           // generation of the current solve
+    unsigned* tri_err = nullptr;    // set by a solve that gave up waiting for a dependency
     int tri_grid = 0;
 
     // banded shared-memory sweeps of the normal-matrix apply (may be null)

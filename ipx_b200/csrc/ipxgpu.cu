@@ -698,6 +698,7 @@ void ipxgpu_destroy(ipxgpu_ctx* c) {
     dev_free(c->peer_dev);
     dev_free(c->fused_bar);
     dev_free(c->tri_ll);
+    dev_free(c->tri_err);
     dev_free(c->fused_tickets);
     dev_free(c->fused_red);
     if (c->band1) { free_band(c->band1); delete c->band1; }
@@ -1325,7 +1326,7 @@ static int cr_host_entry(ipxgpu_ctx* c, int op, bool precond, const double* rhs,
                                cudaMemcpyDeviceToHost));
     if (result)
         result->time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    return IPXGPU_OK;
+    return op == 1 ? check_tri(c) : IPXGPU_OK;
 }
 
 int ipxgpu_pcr_solve(ipxgpu_ctx* c, const double* rhs, double tol, const double* resscale,

@@ -156,7 +156,7 @@ constexpr int kTriBatch = 8;
 constexpr int kTriStash = 2048;  // parked products per warp (16 KB)
 
 __device__ __forceinline__ void tri_row_warp(const TriDev& T, int i, double* x, ulonglong2* ll,
-                                             unsigned gen, int lane, double* stash) {
+                                             unsigned gen, int lane, double* stash, unsigned* err) {
     const int b = T.ptr[i], e = T.ptr[i + 1];
     double v = __ldcg(x + i);
     double d = 0.0;
@@ -207,9 +207,16 @@ __device__ __forceinline__ void tri_row_warp(const TriDev& T, int i, double* x, 
                 const unsigned pending = __ballot_sync(0xffffffffu, !ok);
                 if (pending == 0u) break;
                 if (lane == __ffs(pending) - 1) {
+                    unsigned spins = 0;
                     while (!tri_ll_load(ll + jj, gen, &xj)) {
                         if (pause) __nanosleep(pause);
                         pause = min(2 * pause + 32u, 256u);
+                        // A dependency that never resolves (cannot happen with a valid level
+                        // order) must not hang the GPU: give up after ~2 s and flag the solve.
+                        if (++spins > (1u << 23)) {
+                            *err = 1u;
+                            break;
+                        }
                     }
                     ok = true;
                 }
@@ -259,7 +266,8 @@ __device__ __forceinline__ void tri_row_warp(const TriDev& T, int i, double* x, 
 
 // Whole solve in one cooperative launch (the grid must be co-resident, see above).
 __global__ void __launch_bounds__(kTriWarps * 32, 1)
-tri_syncfree_kernel(TriDev T, double* x, ulonglong2* ll, unsigned gen, const CrState* st) {
+tri_syncfree_kernel(TriDev T, double* x, ulonglong2* ll, unsigned gen, unsigned* err,
+                    const CrState* st) {
     extern __shared__ __align__(16) double tri_stash[];  // kTriWarps * kTriStash
     if (st && st->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -267,7 +275,7 @@ tri_syncfree_kernel(TriDev T, double* x, ulonglong2* ll, unsigned gen, const CrS
     const int nwarps = gridDim.x * kTriWarps;
     double* stash = tri_stash + (size_t)warp * kTriStash;
     for (int r = gwarp; r < T.dim; r += nwarps)
-        tri_row_warp(T, T.order[r], x, ll, gen, lane, stash);
+        tri_row_warp(T, T.order[r], x, ll, gen, lane, stash, err);
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -420,6 +428,8 @@ static int launch_tri(ipxgpu_ctx* c, const TriSystem& T, double* x, const CrStat
                                                                      kTriWarps * 32, smem));
             if (per_sm < 1) return fail(IPXGPU_ERR_STATE, "triangular solve kernel does not fit an SM");
             c->tri_grid = c->num_sms * per_sm;
+            IPXGPU_TRY(dev_alloc(&c->tri_err, 1));
+            IPXGPU_CUDA(cudaMemsetAsync(c->tri_err, 0, sizeof(unsigned), c->stream));
             IPXGPU_TRY(dev_alloc(&c->tri_ll, (size_t)c->m));
             IPXGPU_CUDA(cudaMemsetAsync(c->tri_ll, 0, sizeof(ulonglong2) * (size_t)c->m, c->stream));
             c->tri_gen = 0;
@@ -433,8 +443,9 @@ static int launch_tri(ipxgpu_ctx* c, const TriSystem& T, double* x, const CrStat
         double* xp = x;
         ulonglong2* ll = c->tri_ll;
         unsigned gen = c->tri_gen;
+        unsigned* err = c->tri_err;
         const CrState* stp = st;
-        void* args[] = {&d, &xp, &ll, &gen, &stp};
+        void* args[] = {&d, &xp, &ll, &gen, &err, &stp};
         IPXGPU_CUDA(cudaLaunchCooperativeKernel((void*)tri_syncfree_kernel, dim3(grid),
                                                 dim3(kTriWarps * 32), args,
                                                 (size_t)kTriWarps * kTriStash * sizeof(double),
@@ -454,6 +465,16 @@ static int launch_tri(ipxgpu_ctx* c, const TriSystem& T, double* x, const CrStat
     }
     IPXGPU_CUDA(cudaGetLastError());
     return IPXGPU_OK;
+}
+
+// After a synchronisation: did a triangular solve give up waiting (tri_row_warp)?
+static int check_tri(ipxgpu_ctx* c) {
+    if (!c->tri_err) return IPXGPU_OK;
+    unsigned e = 0;
+    IPXGPU_CUDA(cudaMemcpy(&e, c->tri_err, sizeof e, cudaMemcpyDeviceToHost));
+    if (e == 0) return IPXGPU_OK;
+    cudaMemset(c->tri_err, 0, sizeof e);
+    return fail(IPXGPU_ERR_STATE, "triangular solve: a dependency never resolved");
 }
 
 // lhs(m+1) = C*x, lhs[m] = x'lhs (reference src/splitted_normal_matrix.cc:90-117).
