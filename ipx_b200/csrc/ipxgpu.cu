@@ -365,6 +365,10 @@ static int run_cr_fused(ipxgpu_ctx* c, bool precond, bool zero_start, bool use_r
     F.peers = c->peer_dev;
     F.xmpad = c->xchg_mpad;
     F.xgen_base = c->xchg_gen;
+    {
+        const char* env = std::getenv("IPXGPU_XCHG");
+        F.xll_off = (env && std::string(env) == "pull") ? 0 : c->xchg_ll_off;
+    }
     F.t = c->t;
     F.zero_start = zero_start ? 1 : 0;
     F.sync = GridSync{c->fused_bar, c->fused_red};
@@ -1113,8 +1117,13 @@ int ipxgpu_peer_export(ipxgpu_ctx* c, char handle[64]) {
     if (c->nranks < 2 || c->nranks > 16) return fail(IPXGPU_ERR_STATE, "peer exchange needs 2..16 ranks");
     if (!c->xchg) {
         c->xchg_mpad = ((size_t)c->m + 31) & ~(size_t)31;
-        const size_t bytes = 2 * c->xchg_mpad * sizeof(double) +
-                             (size_t)c->nranks * c->num_sms * sizeof(unsigned);
+        // [pull exchange: y[2][mpad] doubles, flags[nranks][SMs]] [push exchange:
+        // records[2][nranks][mpad] of 16 bytes]
+        size_t bytes = 2 * c->xchg_mpad * sizeof(double) +
+                       (size_t)c->nranks * c->num_sms * sizeof(unsigned);
+        bytes = (bytes + 255) & ~(size_t)255;
+        c->xchg_ll_off = bytes;
+        bytes += 2 * (size_t)c->nranks * c->xchg_mpad * 16;
         IPXGPU_CUDA(cudaMalloc(&c->xchg, bytes));  // plain cudaMalloc: IPC-exportable
         IPXGPU_CUDA(cudaMemset(c->xchg, 0, bytes));
         c->xchg_gen = 0;

@@ -60,7 +60,30 @@ struct FusedArgs {
     double* const* peers;
     size_t xmpad;
     unsigned xgen_base;              // cross-GPU synchronisations before this solve
+    // Push exchange (default): records[2][nranks][xmpad] of 16 bytes at byte offset xll_off of
+    // every rank's buffer; 0 = pull exchange (flags + P2P loads).
+    size_t xll_off;
 };
+
+// 16-byte record of two self-validating 64-bit words {generation | half of the value}: 64-bit
+// words arrive atomically over NVLink (the basis of NCCL's LL protocol), so a reader that
+// finds the generation in both words holds the value - no flag, no fence.sys, no round trip.
+__device__ __forceinline__ void xll_store(ulonglong2* p, unsigned gen, double v) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long w0 = ((unsigned long long)gen << 32) | (bits & 0xffffffffull);
+    const unsigned long long w1 = ((unsigned long long)gen << 32) | (bits >> 32);
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1)
+                 : "memory");
+}
+__device__ __forceinline__ bool xll_load(const ulonglong2* p, unsigned gen, double* val) {
+    unsigned long long w0, w1;
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];"
+                 : "=l"(w0), "=l"(w1)
+                 : "l"(p)
+                 : "memory");
+    *val = __longlong_as_double((long long)(((w1 & 0xffffffffull) << 32) | (w0 & 0xffffffffull)));
+    return (unsigned)(w0 >> 32) == gen && (unsigned)(w1 >> 32) == gen;
+}
 
 constexpr int kFusedStages = 6;
 enum FusedStage : int { kStSweep1 = 0, kStSweep2, kStCombine, kStInit, kStDirection, kStUpdate };
@@ -264,8 +287,63 @@ pcr_fused_kernel(FusedArgs F) {
                 lhs[i] = yv;
                 dot += __dmul_rn(xv, yv);
             }
+        } else if (F.nranks > 1 && F.xll_off != 0) {
+            // Column shards, push exchange: every rank writes its partial product of the slice
+            // straight into every rank's record buffer (posted NVLink stores), then sums the
+            // ranks' records of the slice from its OWN memory in rank order - bit-identical on
+            // all ranks. The records validate themselves (xll_store), so there is no flag, no
+            // fence.sys and no load round trip over NVLink; buffers alternate by generation
+            // parity (a rank can be at most one exchange ahead of a peer).
+            const unsigned gen = F.xgen_base + (unsigned)s_applies;
+            const size_t par = (size_t)(gen & 1u) * (size_t)F.nranks * F.xmpad;
+            for (int i = i0 + tid; i < i1; i += nthr) {
+                double acc = 0.0;
+#pragma unroll 8
+                for (int p = 0; p < nparts; p++) acc += __ldcg(F.T2.partials + (size_t)p * m + i);
+                const double mine = (F.Ws ? __dmul_rn(x[i], F.Ws[i]) : 0.0) + acc;
+                for (int r = 0; r < F.nranks; r++) {
+                    ulonglong2* dst = reinterpret_cast<ulonglong2*>(
+                                          reinterpret_cast<char*>(F.peers[r]) + F.xll_off) +
+                                      par + (size_t)F.rank * F.xmpad + i;
+                    xll_store(dst, gen, mine);
+                }
+            }
+            const ulonglong2* rec = reinterpret_cast<const ulonglong2*>(
+                                        reinterpret_cast<const char*>(F.peers[F.rank]) + F.xll_off) + par;
+            for (int i = i0 + tid; i < i1; i += nthr) {
+                double yv = 0.0;
+                for (int rb = 0; rb < F.nranks; rb += 8) {
+                    double part[8];
+                    bool ok[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        part[u] = 0.0;
+                        ok[u] = rb + u >= F.nranks ||
+                                xll_load(rec + (size_t)(rb + u) * F.xmpad + i, gen, &part[u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        long long spins = 0;
+                        while (!ok[u]) {
+                            ok[u] = xll_load(rec + (size_t)(rb + u) * F.xmpad + i, gen, &part[u]);
+                            if ((++spins & 0xffff) == 0) {
+                                // a peer that never arrives must not hang this GPU
+                                if (spins > (1ll << 24) || __ldcg(F.abort_word) != 0.0) {
+                                    *F.abort_word = 2.0;
+                                    break;
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        if (rb + u < F.nranks) yv += part[u];
+                }
+                lhs[i] = yv;
+                dot += __dmul_rn(x[i], yv);
+            }
         } else if (F.nranks > 1) {
-            // Column shards: this rank's partial product of the slice goes to its
+            // Column shards, pull exchange (IPXGPU_XCHG=pull): this rank's partial product of the slice goes to its
             // exchange buffer; the same CTA of every rank then sums the ranks'
             // partials of the slice in rank order (bit-identical on all ranks)
             // with P2P loads. Synchronisation is per slice: a flag per (rank, CTA)
