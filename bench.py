@@ -341,8 +341,16 @@ def run_gpu(args):
     if world == 1:
         collective = "none"
     elif banded and os.environ.get("IPXGPU_PEER", "1") != "0":
-        collective = ("in-kernel sum of the ranks' partial products over NVLink peer memory "
-                      "(P2P loads, per-slice flags) once per CR iteration")
+        how = os.environ.get("IPXGPU_XCHG", "auto")
+        if how == "pull":
+            collective = ("in-kernel sum of the ranks' partial products over NVLink peer memory "
+                          "(P2P loads, per-slice flags) once per CR iteration")
+        elif how == "two" or (how != "one" and world >= 4):
+            collective = ("in-kernel reduce-scatter + all-gather of self-validating 16-byte records "
+                          "pushed over NVLink peer memory, once per CR iteration")
+        else:
+            collective = ("in-kernel all-to-all of self-validating 16-byte records pushed over "
+                          "NVLink peer memory, summed in rank order, once per CR iteration")
     else:
         collective = "ncclAllReduce(m+1 f64) per CR iteration"
     line = None

@@ -367,7 +367,9 @@ static int run_cr_fused(ipxgpu_ctx* c, bool precond, bool zero_start, bool use_r
     F.xgen_base = c->xchg_gen;
     {
         const char* env = std::getenv("IPXGPU_XCHG");
-        F.xll_off = (env && std::string(env) == "pull") ? 0 : c->xchg_ll_off;
+        const std::string how = env ? env : "auto";
+        F.xll_off = how == "pull" ? 0 : c->xchg_ll_off;
+        F.xtwo_phase = how == "two" || (how != "one" && c->nranks >= 4);
     }
     F.t = c->t;
     F.zero_start = zero_start ? 1 : 0;
@@ -1123,7 +1125,8 @@ int ipxgpu_peer_export(ipxgpu_ctx* c, char handle[64]) {
                        (size_t)c->nranks * c->num_sms * sizeof(unsigned);
         bytes = (bytes + 255) & ~(size_t)255;
         c->xchg_ll_off = bytes;
-        bytes += 2 * (size_t)c->nranks * c->xchg_mpad * 16;
+        bytes += 2 * (size_t)c->nranks * c->xchg_mpad * 16;  // partial-product records
+        bytes += 2 * c->xchg_mpad * 16;                       // final records (two-phase exchange)
         IPXGPU_CUDA(cudaMalloc(&c->xchg, bytes));  // plain cudaMalloc: IPC-exportable
         IPXGPU_CUDA(cudaMemset(c->xchg, 0, bytes));
         c->xchg_gen = 0;
