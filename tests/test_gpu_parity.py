@@ -439,10 +439,13 @@ def test_interrupt_callback(capi):
     ctx.close()
 
 
-def test_sharded_solve_over_nvlink_peer_memory():
+@pytest.mark.parametrize("exchange", ["auto", "two", "pull"])
+def test_sharded_solve_over_nvlink_peer_memory(exchange):
     """Two ranks (one per GPU, torchrun): column shards, the persistent CR kernel sums the
-    ranks' partial products with P2P loads. Needs two GPUs on the box; tools/check_sharded.py
-    compares with the single-GPU solve and checks that all ranks hold identical iterates."""
+    ranks' partial products over NVLink peer memory - one-hop records (auto at 2 ranks), the
+    two-hop reduce-scatter + all-gather of records used from 4 ranks on, and the flag + P2P-load
+    exchange. Needs two GPUs on the box; tools/check_sharded.py compares with the single-GPU
+    solve and checks that all ranks hold identical iterates."""
     import os
     import subprocess
     import sys
@@ -450,8 +453,9 @@ def test_sharded_solve_over_nvlink_peer_memory():
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, IPXGPU_XCHG=exchange)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
                         "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                         "--master-port", "29517", os.path.join(repo, "tools", "check_sharded.py")],
-                       capture_output=True, text=True, timeout=600)
+                       capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "SHARDED PARITY PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
