@@ -172,6 +172,7 @@ struct ipxgpu_ctx {
     void* xchg = nullptr;             // own exchange buffer: y[2][xchg_mpad] doubles, then flags
     size_t xchg_mpad = 0;
     size_t xchg_ll_off = 0;           // byte offset of the push-exchange records in xchg
+    double* xchg_abort = nullptr;     // set by a stand-alone exchange that gave up waiting
     void* peer_base[16] = {nullptr};  // every rank's exchange buffer as mapped here (own: xchg)
     double** peer_dev = nullptr;      // device copy of peer_base
     bool peers_ready = false;

@@ -171,6 +171,16 @@ static int allreduce_sum(ipxgpu_ctx* c, double* buf, size_t count) {
 
 // ------------------------------------------------------------------ operator launches
 
+// Sharded contexts whose ranks exchanged IPC handles sum the partial products with the record
+// exchange; IPXGPU_XCHG=nccl (or pull, which exists in the persistent kernel only) keeps
+// ncclAllReduce for the launch-per-stage loop.
+static bool records_exchange(const ipxgpu_ctx* c) {
+    if (c->nranks < 2 || !c->peers_ready || !c->xchg || !c->xchg_abort) return false;
+    const char* env = std::getenv("IPXGPU_XCHG");
+    if (env && (std::string(env) == "nccl" || std::string(env) == "pull")) return false;
+    return true;
+}
+
 // lhs(m+1) = AI*W*AI'*x restricted to this shard (allreduced when sharded);
 // lhs[m] = x'lhs. `mode`/`slot`/`st` thread the CR scalar step through.
 static int launch_normal_apply_w(ipxgpu_ctx* c, const double* Wc, const double* Ws,
@@ -218,7 +228,31 @@ static int launch_normal_apply_w(ipxgpu_ctx* c, const double* Wc, const double* 
             IPXGPU_TRY(launch_sweep(c, op, c->spill2.tiles, c->spill2.A, sharded ? nullptr : st));
         }
     }
-    if (sharded) {
+    if (sharded && records_exchange(c)) {
+        // Sum over the ranks with the record exchange over NVLink peer memory (pcr_fused.cuh):
+        // every rank launches the same sequence of exchanges, numbered by xchg_gen.
+        const char* env = std::getenv("IPXGPU_XCHG");
+        const std::string how = env ? env : "auto";
+        XchgArgs A;
+        A.y = y;
+        A.x = x;
+        A.m = (int)c->m;
+        A.nranks = c->nranks;
+        A.rank = c->rank;
+        A.peers = c->peer_dev;
+        A.xmpad = c->xchg_mpad;
+        A.xll_off = c->xchg_ll_off;
+        A.gen = ++c->xchg_gen;
+        A.two_phase = how == "two" || (how != "one" && c->nranks >= 4);
+        A.mode = st ? mode : (int)kApplyPlain;
+        A.slot = st ? slot : (int)kSlotNone;
+        A.abort_word = c->xchg_abort;
+        const int grid = grid_for(c, c->m);  // <= 8 CTAs per SM: co-resident
+        IPXGPU_TRY(ensure_reduce(c, grid));
+        xchg_records_kernel<<<grid, kBlock, 0, c->stream>>>(A, c->red, st);
+        c->launches++;
+        IPXGPU_CUDA(cudaGetLastError());
+    } else if (sharded) {
         IPXGPU_TRY(allreduce_sum(c, y, (size_t)c->m + 1));
         if (st && mode != kApplyPlain) {
             cr_after_apply_kernel<<<1, 1, 0, c->stream>>>(y + c->m, mode, slot, st);
@@ -572,6 +606,14 @@ static int run_cr(ipxgpu_ctx* c, int op, bool precond, bool zero_start, bool use
     }
     IPXGPU_CUDA(cudaStreamSynchronize(c->stream));
     IPXGPU_CUDA(cudaMemcpy(&h, c->st_dev, sizeof h, cudaMemcpyDeviceToHost));
+    if (c->nranks > 1 && c->xchg_abort) {
+        double aborted = 0.0;
+        IPXGPU_CUDA(cudaMemcpy(&aborted, c->xchg_abort, sizeof aborted, cudaMemcpyDeviceToHost));
+        if (aborted != 0.0) {
+            cudaMemset(c->xchg_abort, 0, sizeof(double));
+            return fail(IPXGPU_ERR_STATE, "peer exchange timed out: a rank did not arrive");
+        }
+    }
     if (result) {
         result->errflag = interrupted ? interrupted : h.errflag;
         result->iter = h.iter;
@@ -704,6 +746,7 @@ void ipxgpu_destroy(ipxgpu_ctx* c) {
     dev_free(c->peer_dev);
     dev_free(c->fused_bar);
     dev_free(c->tri_ll);
+    dev_free(c->xchg_abort);
     dev_free(c->tri_err);
     dev_free(c->fused_tickets);
     dev_free(c->fused_red);
@@ -1130,6 +1173,8 @@ int ipxgpu_peer_export(ipxgpu_ctx* c, char handle[64]) {
         IPXGPU_CUDA(cudaMalloc(&c->xchg, bytes));  // plain cudaMalloc: IPC-exportable
         IPXGPU_CUDA(cudaMemset(c->xchg, 0, bytes));
         c->xchg_gen = 0;
+        IPXGPU_TRY(dev_alloc(&c->xchg_abort, 1));
+        IPXGPU_CUDA(cudaMemset(c->xchg_abort, 0, sizeof(double)));
     }
     cudaIpcMemHandle_t h;
     IPXGPU_CUDA(cudaIpcGetMemHandle(&h, c->xchg));

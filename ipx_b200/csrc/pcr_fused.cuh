@@ -616,4 +616,93 @@ pcr_fused_kernel(FusedArgs F) {
     }
 }
 
+
+// The record exchange as a kernel of its own, for sharded contexts that run the
+// launch-per-stage CR loop (generic sweeps, e.g. config 5 with m = 10^6): y (this rank's
+// partial product, slack term included on rank 0) becomes the sum over the ranks, in rank
+// order, on every rank; y[m] = x'y; then the scalar step that follows the apply. Replaces
+// ncclAllReduce(m+1) + cr_after_apply_kernel. Same two shapes and the same records as the
+// combine stage of pcr_fused_kernel. Grid-stride; the grid must be co-resident on every rank
+// (<= 8 CTAs per SM), because a thread waits for the peers' threads of the same element.
+struct XchgArgs {
+    double* y;        // m+1
+    const double* x;  // m
+    int m;
+    int nranks, rank;
+    double* const* peers;
+    size_t xmpad, xll_off;
+    unsigned gen;
+    int two_phase;
+    int mode, slot;   // after_apply
+    double* abort_word;
+};
+
+__global__ void __launch_bounds__(kBlock)
+xchg_records_kernel(XchgArgs A, Reduce red, CrState* st) {
+    __shared__ double s_red[kWarps];
+    __shared__ int s_flag;
+    if (st != nullptr && st->done) return;
+    const unsigned gen = A.gen;
+    const size_t par = (size_t)(gen & 1u) * (size_t)A.nranks * A.xmpad;
+    const size_t fin_off = A.xll_off + 2 * (size_t)A.nranks * A.xmpad * 16 +
+                           (size_t)(gen & 1u) * A.xmpad * 16;
+    auto wait_rec = [&](const ulonglong2* p, double* val) {
+        long long spins = 0;
+        while (!xll_load(p, gen, val)) {
+            if ((++spins & 0xffff) == 0) {
+                if (spins > (1ll << 24) || __ldcg(A.abort_word) != 0.0) {
+                    *A.abort_word = 2.0;  // a peer that never arrives must not hang this GPU
+                    break;
+                }
+            }
+        }
+    };
+    const ulonglong2* rec = reinterpret_cast<const ulonglong2*>(
+                                reinterpret_cast<const char*>(A.peers[A.rank]) + A.xll_off) + par;
+    const ulonglong2* fin = reinterpret_cast<const ulonglong2*>(
+        reinterpret_cast<const char*>(A.peers[A.rank]) + fin_off);
+    const int per = (A.m + A.nranks - 1) / A.nranks;  // two-phase: rows [r*per, (r+1)*per) -> rank r
+    double dot = 0.0;
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < A.m; i += gridDim.x * kBlock) {
+        const double mine = A.y[i];
+        double yv = 0.0;
+        if (A.two_phase) {
+            const int owner = i / per;
+            xll_store(reinterpret_cast<ulonglong2*>(reinterpret_cast<char*>(A.peers[owner]) +
+                                                    A.xll_off) + par + (size_t)A.rank * A.xmpad + i,
+                      gen, mine);
+            if (owner == A.rank) {
+                double tot = 0.0;
+                for (int r = 0; r < A.nranks; r++) {
+                    double part;
+                    wait_rec(rec + (size_t)r * A.xmpad + i, &part);
+                    tot += part;
+                }
+                for (int r = 0; r < A.nranks; r++)
+                    xll_store(reinterpret_cast<ulonglong2*>(
+                                  reinterpret_cast<char*>(A.peers[r]) + fin_off) + i, gen, tot);
+            }
+            wait_rec(fin + i, &yv);
+        } else {
+            for (int r = 0; r < A.nranks; r++)
+                xll_store(reinterpret_cast<ulonglong2*>(reinterpret_cast<char*>(A.peers[r]) +
+                                                        A.xll_off) + par + (size_t)A.rank * A.xmpad + i,
+                          gen, mine);
+            for (int r = 0; r < A.nranks; r++) {
+                double part;
+                wait_rec(rec + (size_t)r * A.xmpad + i, &part);
+                yv += part;
+            }
+        }
+        A.y[i] = yv;
+        dot += __dmul_rn(A.x[i], yv);
+    }
+    const double mine_dot = block_sum(dot, s_red);
+    double ts, ts2, tm;
+    if (grid_reduce(red, mine_dot, 0.0, 0.0, s_red, &s_flag, &ts, &ts2, &tm) && threadIdx.x == 0) {
+        A.y[A.m] = ts;
+        if (st && !(A.mode == kApplyPlain && A.slot == kSlotNone)) after_apply(st, A.mode, ts, A.slot);
+    }
+}
+
 }  // namespace ipxgpu
