@@ -340,7 +340,10 @@ def run_gpu(args):
         kernel_name = "band_sweep_kernel (sweep 1) + band_sweep_kernel (sweep 2) + band_combine_kernel"
     if world == 1:
         collective = "none"
-    elif banded and os.environ.get("IPXGPU_PEER", "1") != "0":
+    elif os.environ.get("IPXGPU_PEER", "1") != "0" and (
+            banded or os.environ.get("IPXGPU_XCHG", "auto") not in ("pull", "nccl")):
+        # (without the banded layouts the same record exchange runs as a kernel of its own
+        # in the launch-per-stage CR loop)
         how = os.environ.get("IPXGPU_XCHG", "auto")
         if how == "pull":
             collective = ("in-kernel sum of the ranks' partial products over NVLink peer memory "

@@ -662,40 +662,51 @@ xchg_records_kernel(XchgArgs A, Reduce red, CrState* st) {
     const ulonglong2* fin = reinterpret_cast<const ulonglong2*>(
         reinterpret_cast<const char*>(A.peers[A.rank]) + fin_off);
     const int per = (A.m + A.nranks - 1) / A.nranks;  // two-phase: rows [r*per, (r+1)*per) -> rank r
+    const int first = blockIdx.x * kBlock + threadIdx.x, stride = gridDim.x * kBlock;
     double dot = 0.0;
-    for (int i = blockIdx.x * kBlock + threadIdx.x; i < A.m; i += gridDim.x * kBlock) {
-        const double mine = A.y[i];
-        double yv = 0.0;
-        if (A.two_phase) {
-            const int owner = i / per;
-            xll_store(reinterpret_cast<ulonglong2*>(reinterpret_cast<char*>(A.peers[owner]) +
+    // Three passes over this thread's elements, so that its pushes, its sums and its final
+    // reads are each in flight together (one NVLink hop per pass, not per element).
+    if (A.two_phase) {
+        for (int i = first; i < A.m; i += stride)
+            xll_store(reinterpret_cast<ulonglong2*>(reinterpret_cast<char*>(A.peers[i / per]) +
                                                     A.xll_off) + par + (size_t)A.rank * A.xmpad + i,
-                      gen, mine);
-            if (owner == A.rank) {
-                double tot = 0.0;
-                for (int r = 0; r < A.nranks; r++) {
-                    double part;
-                    wait_rec(rec + (size_t)r * A.xmpad + i, &part);
-                    tot += part;
-                }
-                for (int r = 0; r < A.nranks; r++)
-                    xll_store(reinterpret_cast<ulonglong2*>(
-                                  reinterpret_cast<char*>(A.peers[r]) + fin_off) + i, gen, tot);
+                      gen, A.y[i]);
+        for (int i = first; i < A.m; i += stride) {
+            if (i / per != A.rank) continue;
+            double tot = 0.0;
+            for (int r = 0; r < A.nranks; r++) {
+                double part;
+                wait_rec(rec + (size_t)r * A.xmpad + i, &part);
+                tot += part;
             }
+            for (int r = 0; r < A.nranks; r++)
+                xll_store(reinterpret_cast<ulonglong2*>(reinterpret_cast<char*>(A.peers[r]) + fin_off) + i,
+                          gen, tot);
+        }
+        for (int i = first; i < A.m; i += stride) {
+            double yv;
             wait_rec(fin + i, &yv);
-        } else {
+            A.y[i] = yv;
+            dot += __dmul_rn(A.x[i], yv);
+        }
+    } else {
+        for (int i = first; i < A.m; i += stride) {
+            const double mine = A.y[i];
             for (int r = 0; r < A.nranks; r++)
                 xll_store(reinterpret_cast<ulonglong2*>(reinterpret_cast<char*>(A.peers[r]) +
                                                         A.xll_off) + par + (size_t)A.rank * A.xmpad + i,
                           gen, mine);
+        }
+        for (int i = first; i < A.m; i += stride) {
+            double yv = 0.0;
             for (int r = 0; r < A.nranks; r++) {
                 double part;
                 wait_rec(rec + (size_t)r * A.xmpad + i, &part);
                 yv += part;
             }
+            A.y[i] = yv;
+            dot += __dmul_rn(A.x[i], yv);
         }
-        A.y[i] = yv;
-        dot += __dmul_rn(A.x[i], yv);
     }
     const double mine_dot = block_sum(dot, s_red);
     double ts, ts2, tm;
