@@ -32,6 +32,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -510,6 +511,27 @@ inline bool band_finish_plan(BandPlan* P) {
     return P->smem <= 227 * 1024;
 }
 
+// Runs fn(begin, end) over [0, n) on up to `threads` host threads (contiguous ranges).
+template <class F>
+inline void band_parallel_for(size_t n, int threads, F fn) {
+    threads = (int)std::min<size_t>((size_t)std::max(1, threads), std::max<size_t>(1, n));
+    if (threads <= 1) {
+        fn((size_t)0, n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    for (int k = 0; k < threads; k++) {
+        const size_t b = n * k / threads, e = n * (k + 1) / threads;
+        pool.emplace_back([=] { fn(b, e); });
+    }
+    for (std::thread& t : pool) t.join();
+}
+
+inline int band_build_threads() {
+    const unsigned hw = std::thread::hardware_concurrency();
+    return (int)std::min(8u, std::max(1u, hw / 2));  // two sweeps are built side by side
+}
+
 // Re-tiles a compressed structure (segments ptr[0..S], gather indices idx in
 // [0,V), ascending per segment) into the banded row streams. Returns false when
 // a run is longer than max_run (such structures suit the generic sweep).
@@ -558,50 +580,66 @@ inline bool band_build(const BandPlan& P, const int* ptr, const int* idx, const 
     // to synchronise with each other between tiles.
     const size_t ntw = ntiles * (size_t)NW;
     std::vector<long long> tcount(ntw + 1, 0);
-    for (int s = 0; s < S; s++) {
-        if (any_skip && skip[s]) continue;
-        const size_t trow = (size_t)(s / SB) * NVB;
-        const int w = (s % SB) % NW;
-        int p = ptr[s];
-        const int pe = ptr[s + 1];
-        while (p < pe) {
-            const int vb = idx[p] / VB;
-            int q = p + 1;
-            while (q < pe && idx[q] / VB == vb) q++;
-            if (q - p > max_run) return false;
-            tcount[(trow + vb) * NW + w + 1]++;
-            p = q;
+    const int nthreads = band_build_threads();
+    // The tiles of different segment blocks are disjoint: blocks are counted (and below
+    // scattered) side by side; inside a tile the runs keep their segment order.
+    std::vector<char> too_long((size_t)NSB, 0);
+    band_parallel_for((size_t)NSB, nthreads, [&](size_t sb_begin, size_t sb_end) {
+        for (size_t sb = sb_begin; sb < sb_end; sb++) {
+            const int s_end = (int)std::min<long long>(S, (long long)(sb + 1) * SB);
+            for (int s = (int)sb * SB; s < s_end; s++) {
+                if (any_skip && skip[s]) continue;
+                const size_t trow = sb * NVB;
+                const int w = (s % SB) % NW;
+                int p = ptr[s];
+                const int pe = ptr[s + 1];
+                while (p < pe) {
+                    const int vb = idx[p] / VB;
+                    int q = p + 1;
+                    while (q < pe && idx[q] / VB == vb) q++;
+                    if (q - p > max_run) too_long[sb] = 1;
+                    tcount[(trow + vb) * NW + w + 1]++;
+                    p = q;
+                }
+            }
         }
-    }
+    });
+    for (char f : too_long)
+        if (f) return false;
     for (size_t t = 0; t < ntw; t++) tcount[t + 1] += tcount[t];
     std::vector<Run> runs((size_t)tcount[ntw]);
     {
         std::vector<long long> next(tcount.begin(), tcount.end() - 1);
-        for (int s = 0; s < S; s++) {
-            if (any_skip && skip[s]) continue;
-            const size_t trow = (size_t)(s / SB) * NVB;
-            const int w = (s % SB) % NW;
-            int p = ptr[s];
-            const int pe = ptr[s + 1];
-            while (p < pe) {
-                const int vb = idx[p] / VB;
-                int q = p + 1;
-                while (q < pe && idx[q] / VB == vb) q++;
-                runs[(size_t)next[(trow + vb) * NW + w]++] =
-                    Run{p, (unsigned short)(s % SB), (unsigned short)(q - p)};
-                p = q;
+        band_parallel_for((size_t)NSB, nthreads, [&](size_t sb_begin, size_t sb_end) {
+            for (size_t sb = sb_begin; sb < sb_end; sb++) {
+                const int s_end = (int)std::min<long long>(S, (long long)(sb + 1) * SB);
+                for (int s = (int)sb * SB; s < s_end; s++) {
+                    if (any_skip && skip[s]) continue;
+                    const size_t trow = sb * NVB;
+                    const int w = (s % SB) % NW;
+                    int p = ptr[s];
+                    const int pe = ptr[s + 1];
+                    while (p < pe) {
+                        const int vb = idx[p] / VB;
+                        int q = p + 1;
+                        while (q < pe && idx[q] / VB == vb) q++;
+                        runs[(size_t)next[(trow + vb) * NW + w]++] =
+                            Run{p, (unsigned short)(s % SB), (unsigned short)(q - p)};
+                        p = q;
+                    }
+                }
             }
-        }
+        });
     }
     // pass 2: deal the runs of every (tile, warp) to the 32 lanes, longest
     // first, each to the least loaded lane (ties: lowest lane), so loads differ
     // by <= 1 whenever there are enough short runs. place[r] = lane << 16 | offset.
     std::vector<uint32_t> place(runs.size());
     std::vector<int> trows(ntw, 0);  // rows of (tile, warp)
-    {
+    band_parallel_for(ntw, nthreads, [&](size_t t_begin, size_t t_end) {
         std::vector<long long> order;
         std::vector<int> bucket_start;
-        for (size_t t = 0; t < ntw; t++) {
+        for (size_t t = t_begin; t < t_end; t++) {
             const long long r0 = tcount[t], r1 = tcount[t + 1];
             const int nr = (int)(r1 - r0);
             if (nr == 0) continue;
@@ -627,7 +665,7 @@ inline bool band_build(const BandPlan& P, const int* ptr, const int* idx, const 
             for (int l = 0; l < 32; l++) mx = std::max(mx, load[l]);
             trows[t] = mx;
         }
-    }
+    });
     // pass 3: row offsets in stream order (item, warp, step)
     const int K = P.K, nparts = P.nparts;
     H->row_ptr.assign((size_t)P.nitems * NW * (K + 1), 0);
@@ -660,28 +698,34 @@ inline bool band_build(const BandPlan& P, const int* ptr, const int* idx, const 
     H->stream.assign((size_t)rows_alloc * 96, 0u);
     {
         const uint32_t padkey = ((uint32_t)SB << 16) | kBandLast;
-        for (long long r = 0; r < rows; r++) {
-            uint32_t* row = H->stream.data() + (size_t)r * 96;
-            for (int l = 0; l < 32; l++) row[l] = padkey;
-        }
-    }
-    long long filled = 0;
-    for (size_t t = 0; t < ntw; t++) {
-        const int vb = (int)((t / NW) % NVB);
-        for (long long r = tcount[t]; r < tcount[t + 1]; r++) {
-            const Run& R = runs[r];
-            const int l = (int)(place[r] >> 16), off = (int)(place[r] & 0xffffu);
-            const long long row0 = tile_warp_row[t] + off;
-            for (int j = 0; j < R.len; j++) {
-                uint32_t* row = H->stream.data() + (size_t)(row0 + j) * 96;
-                uint32_t key = ((uint32_t)R.seg << 16) | (uint32_t)(idx[R.first + j] - vb * VB);
-                if (j == R.len - 1) key |= kBandLast;
-                row[l] = key;
-                reinterpret_cast<double*>(row + 32)[l] = val[R.first + j];
+        uint32_t* base = H->stream.data();
+        band_parallel_for((size_t)rows, nthreads, [=](size_t r_begin, size_t r_end) {
+            for (size_t r = r_begin; r < r_end; r++) {
+                uint32_t* row = base + r * 96;
+                for (int l = 0; l < 32; l++) row[l] = padkey;
             }
-            filled += R.len;
-        }
+        });
     }
+    // every (tile, warp) owns its rows: the tiles are filled independently
+    band_parallel_for(ntw, nthreads, [&](size_t t_begin, size_t t_end) {
+        for (size_t t = t_begin; t < t_end; t++) {
+            const int vb = (int)((t / NW) % NVB);
+            for (long long r = tcount[t]; r < tcount[t + 1]; r++) {
+                const Run& R = runs[r];
+                const int l = (int)(place[r] >> 16), off = (int)(place[r] & 0xffffu);
+                const long long row0 = tile_warp_row[t] + off;
+                for (int j = 0; j < R.len; j++) {
+                    uint32_t* row = H->stream.data() + (size_t)(row0 + j) * 96;
+                    uint32_t key = ((uint32_t)R.seg << 16) | (uint32_t)(idx[R.first + j] - vb * VB);
+                    if (j == R.len - 1) key |= kBandLast;
+                    row[l] = key;
+                    reinterpret_cast<double*>(row + 32)[l] = val[R.first + j];
+                }
+            }
+        }
+    });
+    long long filled = 0;
+    for (const Run& R : runs) filled += R.len;
     H->pad_entries = rows * 32 - filled;
     return true;
 }
