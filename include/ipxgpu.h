@@ -99,15 +99,19 @@ int ipxgpu_partition_columns(int64_t n, const int64_t* AIp, int32_t nranks,
                              int64_t* bounds);
 int ipxgpu_comm_unique_id(char id[128]);
 int ipxgpu_comm_init(ipxgpu_ctx* ctx, const char id[128]);
-/* Peer exchange over NVLink for the persistent CR kernel (optional; without it
- * a sharded CR solve runs one launch per stage with an NCCL allreduce per
- * iteration). Every rank exports the IPC handle of its exchange buffer
- * (ipxgpu_peer_export), the caller gathers the nranks handles in rank order
- * (e.g. with torch.distributed.all_gather) and every rank imports them
- * (ipxgpu_peer_import). The kernel then sums the ranks' partial products with
- * P2P loads from the peers' buffers, slice by slice, with per-slice flags in
- * peer memory instead of a collective. One process per GPU, all GPUs of one
- * NVLink domain. */
+/* Peer exchange over NVLink (optional; without it a sharded CR solve runs one
+ * launch per stage with an NCCL allreduce per iteration). Every rank exports
+ * the IPC handle of its exchange buffer (ipxgpu_peer_export), the caller
+ * gathers the nranks handles in rank order (e.g. with
+ * torch.distributed.all_gather) and every rank imports them
+ * (ipxgpu_peer_import). The ranks' partial products then cross NVLink as
+ * self-validating 16-byte records written straight into the peers' buffers
+ * and summed in rank order by the receiver - inside the persistent CR kernel,
+ * or by a small kernel of its own in the launch-per-stage loop - instead of a
+ * collective (env IPXGPU_XCHG=pull|one|two|nccl selects
+ * other exchange shapes). One process per GPU, all GPUs of one NVLink domain.
+ * Replaces nothing in the reference (it has no multi-device path); it is the
+ * one exchange step of the column-sharded A*D^2*A' (SURVEY.md section 8e). */
 int ipxgpu_peer_export(ipxgpu_ctx* ctx, char handle[64]);
 int ipxgpu_peer_import(ipxgpu_ctx* ctx, const char* handles);
 
