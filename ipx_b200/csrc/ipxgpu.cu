@@ -667,9 +667,6 @@ struct Warmup {
     int device = -1, ndev = 0;
     cudaError_t err = cudaSuccess;
     double ms = 0.0;
-    ~Warmup() {
-        if (th.joinable()) th.join();
-    }
     void start(int dev_hint) {
         std::lock_guard<std::mutex> lock(mu);
         if (started) return;
@@ -702,9 +699,11 @@ struct Warmup {
         }
     }
 };
+// Never destroyed: a process that exits while the helper thread is still inside the CUDA
+// initialisation must neither wait for it nor run a std::thread destructor on it.
 Warmup& warmup() {
-    static Warmup w;
-    return w;
+    static Warmup* w = new Warmup;
+    return *w;
 }
 }  // namespace
 
