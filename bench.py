@@ -181,7 +181,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "cr_matvecs_per_sec", "value": value, "unit": "matvec/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "strong" if STRONG else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(1).replace(f"{ITERS} iterations",
                                                         f"{REF_ITERS} iterations")},
