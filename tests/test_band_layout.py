@@ -93,3 +93,15 @@ def test_small_problems_are_not_planned_without_force(capi):
     for sweep in ("sweep1", "sweep2"):
         if r[sweep]["planned"]:
             assert r[sweep]["err"] <= 1e-10
+
+
+def test_threaded_build_is_deterministic(capi):
+    """The layout is built on several host threads (segment blocks and tiles are independent):
+    two builds of the same matrix must agree exactly (same padding, same stream contents as seen
+    through the host walk)."""
+    lp = lpgen.random_sparse_lp(20000, 400000, 10, 35)
+    x = np.random.default_rng(4).standard_normal(lp.m)
+    a = capi.band_selftest(lp.m, lp.n, *_structural(lp), x)
+    b = capi.band_selftest(lp.m, lp.n, *_structural(lp), x)
+    assert a == b
+    assert a["sweep1"]["planned"] == 1.0 and a["sweep2"]["planned"] == 1.0
