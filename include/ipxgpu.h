@@ -241,6 +241,33 @@ int ipxgpu_split_prepare(ipxgpu_ctx* ctx, const double* nonbasic_scale,
 int ipxgpu_split_apply(ipxgpu_ctx* ctx, const double* rhs, double* lhs,
                        double* rhs_dot_lhs);
 
+/* ---- KKTSolverBasis (reference src/kkt_solver_basis.cc) ---- */
+
+/* What _Solve needs on top of ipxgpu_lu_load + ipxgpu_split_prepare (i.e. after
+ * SplittedNormalMatrix::Prepare, src/kkt_solver_basis.cc:64), m entries each:
+ * basic_var[k] = basis[colperm[k]], the variable at pivot position k;
+ * colperm[k] = its basis position (src/basis.h:109-118);
+ * basic_scale[k] = colscale[basic_var[k]] for BASIC variables and 1 for
+ * BASIC_FREE ones (the positions listed as free in ipxgpu_split_prepare).
+ * Unsharded contexts only. */
+int ipxgpu_kktbasis_prepare(ipxgpu_ctx* ctx, const int64_t* basic_var,
+                            const int64_t* colperm, const double* basic_scale);
+/* Basis::SolveDense on the fresh factorization (src/basis.cc:168-170, reached
+ * from src/kkt_solver_basis.cc:97,121,124,175,191): lhs = inverse(B) rhs
+ * (trans 'N': rhs indexed by row, lhs by basis position) or inverse(B') rhs
+ * ('T': rhs by basis position, lhs by row), as permutations + the triangular
+ * solves on the loaded factors. Host vectors of m entries. */
+int ipxgpu_basis_solve(ipxgpu_ctx* ctx, char trans, const double* rhs,
+                       double* lhs);
+/* _Solve (src/kkt_solver_basis.cc:75-194): right-hand side through the masked
+ * sweeps over the NONBASIC columns, SolveDense steps, unpreconditioned CR on
+ * the split operator from y = 0, recovery of (x, y). a, x: host n+m; b, y:
+ * host m. result->time_NNt/_B/_Bt carry the device times of the CR loop. */
+int ipxgpu_kktbasis_solve(ipxgpu_ctx* ctx, const double* a, const double* b,
+                          double tol, int64_t maxiter, double* x, double* y,
+                          ipxgpu_cr_result* result,
+                          ipxgpu_interrupt_fn interrupt, void* user);
+
 /* ---- measurement helpers ---- */
 
 /* Runs `reps` device-resident normal-matrix applies on resident vectors and

@@ -1,7 +1,7 @@
 """Build recipes for the native parts of ipx_b200 (in-tree, sm_100a only).
 
 * ``ipx_b200/_build/libipxgpu.so``   CUDA kernels + C ABI (include/ipxgpu.h); needs nvcc only.
-* ``ipx_b200/_build/libipx_gpu.so``  IPX with the five hot-path TUs replaced by the GPU
+* ``ipx_b200/_build/libipx_gpu.so``  IPX with the six hot-path TUs replaced by the GPU
   drop-ins of ipx_b200/host; needs the reference tree (compiled against its
   UNMODIFIED headers), so it is built where /root/reference exists and travels
   to the GPU box as a prebuilt file.
@@ -24,10 +24,8 @@ LIBIPXGPU = os.path.join(OUT, "libipxgpu.so")
 LIBIPX_GPU = os.path.join(OUT, "libipx_gpu.so")
 
 # Reference TUs replaced by ipx_b200/host/*_gpu.cc.
-# kkt_solver_basis.cc stays the reference's TU: its _Solve reaches the device through the
-# replaced ConjugateResiduals / SplittedNormalMatrix, its basis maintenance is host work.
 REPLACED = ["normal_matrix", "diagonal_precond", "conjugate_residuals", "splitted_normal_matrix",
-            "kkt_solver_diag"]
+            "kkt_solver_diag", "kkt_solver_basis"]
 ABSENT = ["basiclu_wrapper", "basiclu_kernel"]  # need the un-vendored BASICLU
 SHIMS = ["lu_provider", "sparse_lu", "lapack_min", "ipx_harness"]
 

@@ -40,7 +40,7 @@ EXPORTS = ("ipxgpu_default_options ipxgpu_last_error ipxgpu_device_count ipxgpu_
            "ipxgpu_normal_apply_dev ipxgpu_diag_factorize ipxgpu_diag_get ipxgpu_diag_set "
            "ipxgpu_diag_apply ipxgpu_pcr_solve ipxgpu_pcr_solve_dev ipxgpu_cr_solve ipxgpu_kktdiag_factorize "
            "ipxgpu_kktdiag_solve ipxgpu_lu_load ipxgpu_tri_solve ipxgpu_split_prepare "
-           "ipxgpu_split_apply ipxgpu_time_normal_apply ipxgpu_launch_count ipxgpu_band_selftest ipxgpu_peer_export ipxgpu_peer_import").split()
+           "ipxgpu_split_apply ipxgpu_kktbasis_prepare ipxgpu_basis_solve ipxgpu_kktbasis_solve ipxgpu_time_normal_apply ipxgpu_launch_count ipxgpu_band_selftest ipxgpu_peer_export ipxgpu_peer_import").split()
 
 _lib = None
 
@@ -287,6 +287,24 @@ class Context:
         rhs, lhs, dot = _f64(rhs), np.empty(self.m), C.c_double(np.nan)
         _check(self.lib.ipxgpu_split_apply(self.h, _d(rhs), _d(lhs), C.byref(dot)))
         return lhs, dot.value
+
+    # ---- KKTSolverBasis ----
+    def kktbasis_prepare(self, basic_var, colperm, basic_scale):
+        v, p, s = _i64(basic_var), _i64(colperm), _f64(basic_scale)
+        _check(self.lib.ipxgpu_kktbasis_prepare(self.h, _i(v), _i(p), _d(s)))
+
+    def basis_solve(self, rhs, trans):
+        rhs, lhs = _f64(rhs), np.empty(self.m)
+        _check(self.lib.ipxgpu_basis_solve(self.h, C.c_char(trans.encode()), _d(rhs), _d(lhs)))
+        return lhs
+
+    def kktbasis_solve(self, a, b, tol, maxiter):
+        a, b = _f64(a), _f64(b)
+        x, y, res = np.empty(self.n + self.m), np.empty(self.m), CrResult()
+        _check(self.lib.ipxgpu_kktbasis_solve(self.h, _d(a), _d(b), C.c_double(tol), i64(maxiter),
+                                              _d(x), _d(y), C.byref(res),
+                                              C.cast(None, INTERRUPT_FN), None))
+        return x, y, res.asdict()
 
     # ---- measurement ----
     def time_normal_apply(self, reps, flush_l2=True):

@@ -75,6 +75,14 @@ struct SplitOperator {
     double* work = nullptr;    // m
     double* xun = nullptr;     // m
     double* yun = nullptr;     // m+1
+    // KKTSolverBasis::_Solve on the device (ipxgpu_kktbasis_prepare)
+    bool kkt_ready = false;
+    int num_free = 0;
+    int* basic_var = nullptr;     // m: variable j = basis[colperm[k]] at pivot position k
+    int* colperm = nullptr;       // m: basis position p = colperm[k]
+    double* basic_scale = nullptr;  // m: colscale[j] of BASIC positions, 1 for BASIC_FREE
+    double* tk = nullptr;         // m, pivot-position space
+    double* wrow = nullptr;       // m, row space
 };
 
 __device__ __forceinline__ void tri_row(const TriDev& T, int i, double* x) {
@@ -327,6 +335,77 @@ square_kernel(long long n, const double* __restrict__ a, double* __restrict__ ou
         out[j] = __dmul_rn(a[j], a[j]);
 }
 
+// ---- elementwise steps of KKTSolverBasis::_Solve (reference src/kkt_solver_basis.cc:75-194) ----
+// k = pivot position, j = basic_var[k] the variable there, d = basic_scale[k]. The resident U
+// carries the column scales of the BASIC variables (SplittedNormalMatrix::Prepare,
+// src/splitted_normal_matrix.cc:30-39), so with Us = U D:  inverse(B) v = D Us^{-1} L^{-1} P v and
+// inverse(B') v = P' L^{-T} Us^{-T} D v; the divisions / multiplications by d of :128-137 and
+// :166-177 cancel against that D and are not performed.
+
+// out[k] = free[k] ? a[basic_var[k]] : (src ? src[k] : 0)   (:88-96 with src == nullptr, :165-177)
+__global__ void __launch_bounds__(kBlock)
+kb_slot_free_kernel(int m, const int* __restrict__ basic_var, const unsigned char* __restrict__ free_mask,
+                    const double* __restrict__ a, const double* __restrict__ src,
+                    double* __restrict__ out) {
+    for (int k = blockIdx.x * kBlock + threadIdx.x; k < m; k += gridDim.x * kBlock)
+        out[k] = free_mask[k] ? a[basic_var[k]] : (src ? src[k] : 0.0);
+}
+
+// Slack part of the masked column sweeps: us[i] = nb2s[i] * (as[i] - (w ? w[i] : 0)); then
+// init[i] = sign > 0 ? us[i] : b[i] - us[i]  (:100-119, :180-189 for the identity columns).
+__global__ void __launch_bounds__(kBlock)
+kb_slack_kernel(int m, const double* __restrict__ nb2s, const double* __restrict__ as,
+                const double* __restrict__ w, const double* __restrict__ b, double sign,
+                double* __restrict__ us, double* __restrict__ init) {
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < m; i += gridDim.x * kBlock) {
+        const double u = __dmul_rn(nb2s[i], as[i] - (w ? w[i] : 0.0));
+        us[i] = u;
+        init[i] = sign > 0 ? u : b[i] - u;
+    }
+}
+
+// dst[perm[i]] = src[i] - (sub ? sub[i] : 0)
+__global__ void __launch_bounds__(kBlock)
+kb_scatter_sub_kernel(int m, const int* __restrict__ perm, const double* __restrict__ src,
+                      const double* __restrict__ sub, double* __restrict__ dst) {
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < m; i += gridDim.x * kBlock)
+        dst[perm[i]] = src[i] - (sub ? sub[i] : 0.0);
+}
+
+// CR right-hand side (:128-141): rhs[k] = free ? 0 : t[k] + a[j] * d.
+__global__ void __launch_bounds__(kBlock)
+kb_cr_rhs_kernel(int m, const int* __restrict__ basic_var, const double* __restrict__ basic_scale,
+                 const unsigned char* __restrict__ free_mask, const double* __restrict__ a,
+                 const double* __restrict__ t, double* __restrict__ rhs) {
+    for (int k = blockIdx.x * kBlock + threadIdx.x; k < m; k += gridDim.x * kBlock)
+        rhs[k] = free_mask[k] ? 0.0 : t[k] + __dmul_rn(a[basic_var[k]], basic_scale[k]);
+}
+
+// x[basic_var[k]] = d * t[k]   (:191-193)
+__global__ void __launch_bounds__(kBlock)
+kb_scatter_basic_kernel(int m, const int* __restrict__ basic_var,
+                        const double* __restrict__ basic_scale, const double* __restrict__ t,
+                        double* __restrict__ x) {
+    for (int k = blockIdx.x * kBlock + threadIdx.x; k < m; k += gridDim.x * kBlock)
+        x[basic_var[k]] = __dmul_rn(basic_scale[k], t[k]);
+}
+
+// dst[k] = src[perm[k]] * scale[k]
+__global__ void __launch_bounds__(kBlock)
+kb_gather_scale_kernel(int m, const int* __restrict__ perm, const double* __restrict__ scale,
+                       const double* __restrict__ src, double* __restrict__ dst) {
+    for (int k = blockIdx.x * kBlock + threadIdx.x; k < m; k += gridDim.x * kBlock)
+        dst[k] = __dmul_rn(src[perm[k]], scale[k]);
+}
+
+// dst[perm[k]] = src[k] * scale[k]
+__global__ void __launch_bounds__(kBlock)
+kb_scatter_scale_kernel(int m, const int* __restrict__ perm, const double* __restrict__ scale,
+                        const double* __restrict__ src, double* __restrict__ dst) {
+    for (int k = blockIdx.x * kBlock + threadIdx.x; k < m; k += gridDim.x * kBlock)
+        dst[perm[k]] = __dmul_rn(src[k], scale[k]);
+}
+
 // ---- host side ----
 
 static int ensure_reduce(ipxgpu_ctx* c, int grid);
@@ -354,6 +433,11 @@ static void destroy_split(ipxgpu_ctx* c) {
     dev_free(S->work);
     dev_free(S->xun);
     dev_free(S->yun);
+    dev_free(S->basic_var);
+    dev_free(S->colperm);
+    dev_free(S->basic_scale);
+    dev_free(S->tk);
+    dev_free(S->wrow);
     delete S;
     c->split = nullptr;
 }

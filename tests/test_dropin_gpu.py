@@ -184,6 +184,32 @@ def test_kkt_solver_basis(pair):
     assert rel_err(x1, x0) <= 1e-6
 
 
+def test_kkt_solver_basis_with_free_variables(pair):
+    """BASIC_FREE positions (src/kkt_solver_basis.cc:88-98, :131-137, :166-174) on both arms."""
+    lp, ref, gpu = pair
+    m, n = ref.m, ref.n
+    _, _, lb, ub = ref.model_vectors()
+    it = _iterate(m, n, lb, ub, 14)
+    rng = np.random.default_rng(15)
+    a, b = rng.standard_normal(n + m), rng.standard_normal(m)
+    colweights = 1.0 / (it[4] / it[1] + it[5] / it[2] + 1e-30)
+    out = []
+    for mdl in (ref, gpu):
+        mdl.iterate_set(*it)
+        mdl.basis_from_weights(colweights)
+        basis, _ = mdl.basis_get()
+        for p in (0, m // 2):
+            mdl.basis_free_variable(int(basis[p]))
+        f = mdl.kktbasis_factorize()
+        assert f["err"] == 0
+        out.append(mdl.kktbasis_solve(a, b, 1e-9))
+    (x0, y0, i0), (x1, y1, i1) = out
+    assert i0["err"] == i1["err"] == 0
+    assert abs(i0["kktiter2"] - i1["kktiter2"]) <= 1
+    assert rel_err(y1, y0) <= 1e-6
+    assert rel_err(x1, x0) <= 1e-6
+
+
 LP_CASES = {
     "afiro": (lpgen.afiro_lp, {}),
     "random_500x5000": (lambda: lpgen.random_sparse_lp(500, 5000, 10, 7), {"dualize": 0}),

@@ -131,3 +131,92 @@ def test_split_apply_and_cr(capi, oracle, shape):
         assert info["iter"] == info0["iter"]
     assert info["time_B"] > 0 and info["time_Bt"] > 0 and info["time_NNt"] > 0
     ctx.close()
+
+
+def _basis_setup(reflib, capi, lp, seed, num_free):
+    """A real basis of `lp` (crash basis of the reference's Basis object with the host LU
+    provider) loaded into a device context the way SplittedNormalMatrix::Prepare and
+    KKTSolverBasis::_Factorize do (src/splitted_normal_matrix.cc:18-66,
+    src/kkt_solver_basis.cc:59-65)."""
+    rng = np.random.default_rng(seed)
+    mdl = reflib.model(lp, dualize=0)
+    m, n = mdl.m, mdl.n
+    colscale = np.exp(rng.uniform(-2, 2, n + m))
+    mdl.basis_from_weights(colscale)
+    basis, status = mdl.basis_get()          # status: 0 basic, -1 nonbasic (src/basis.h:57-66)
+    (Lp, Li, Lx), (Up, Ui, Ux), rowperm, colperm = mdl.basis_lu()
+    rowperm_inv = np.empty(m, np.int64)
+    rowperm_inv[rowperm] = np.arange(m)
+    basic_var = basis[colperm]
+    free_positions = np.sort(rng.choice(m, size=num_free, replace=False)).astype(np.int64)
+    is_free = np.zeros(m, bool)
+    is_free[free_positions] = True
+    basic_scale = np.where(is_free, 1.0, colscale[basic_var])
+    Ux_scaled = Ux * np.repeat(basic_scale, np.diff(Up))
+    nonbasic = status < 0
+    nonbasic_scale = np.where(nonbasic, colscale, 0.0)
+    AIp, AIi, AIx = mdl.AI()
+    ctx = capi.Context(m, n, AIp, AIi, AIx)
+    ctx.lu_load((Lp, Li, Lx), (Up, Ui, Ux_scaled))
+    ctx.split_prepare(nonbasic_scale, rowperm_inv, free_positions)
+    ctx.kktbasis_prepare(basic_var, colperm, basic_scale)
+    AI = sp.csc_matrix((AIx, AIi, AIp), shape=(m, n + m))
+    return mdl, ctx, AI, basis, basic_var, colperm, colscale, nonbasic, is_free
+
+
+@pytest.mark.parametrize("shape", [(60, 300, 4), (3000, 20000, 6)])
+def test_basis_solve_dense_on_device(capi, reflib, shape):
+    """ipxgpu_basis_solve = Basis::SolveDense (src/basis.cc:168-170) on the loaded factors."""
+    m, n, k = shape
+    lp = lpgen.random_sparse_lp(m, n, k, 71)
+    mdl, ctx, AI, basis, *_ = _basis_setup(reflib, capi, lp, 72, num_free=max(1, m // 40))
+    B = AI[:, basis].tocsc()
+    rhs = np.random.default_rng(73).standard_normal(m)
+    for trans in ("N", "T"):
+        want = mdl.basis_solve_dense(rhs, trans)
+        got = ctx.basis_solve(rhs, trans)
+        assert rel_err(got, want) <= 1e-10, trans
+        resid = (B @ got if trans == "N" else B.T @ got) - rhs
+        assert np.abs(resid).max() <= 1e-9 * (1.0 + np.abs(got).max() * np.abs(B).max())
+    ctx.close()
+    mdl.close()
+
+
+def test_kktbasis_solve_against_dense_kkt(capi, reflib):
+    """The whole KKTSolverBasis::_Solve on the device against a dense solve of the KKT system
+    it reduces (src/kkt_solver.h:20-39): [G AI'; AI 0] (x, y) = (a, b) with G = diag(1/s^2),
+    G = 0 for free basic variables and x = 0 for fixed nonbasic ones."""
+    m, n = 50, 160
+    lp = lpgen.random_sparse_lp(m, n, 4, 81)
+    mdl, ctx, AI, basis, basic_var, colperm, colscale, nonbasic, is_free = \
+        _basis_setup(reflib, capi, lp, 82, num_free=3)
+    rng = np.random.default_rng(83)
+    # a few nonbasic variables are "fixed" (scale 0, src/kkt_solver_basis.cc:381-383): they are
+    # exactly the nonbasic columns whose scale was masked; re-prepare with them masked
+    nb = np.nonzero(nonbasic)[0]
+    fixed = rng.choice(nb, size=5, replace=False)
+    g = 1.0 / colscale**2
+    g[basic_var[is_free]] = 0.0
+    keep = np.ones(n + m, bool)
+    keep[fixed] = False
+    nonbasic_scale = np.where(nonbasic & keep, colscale, 0.0)
+    rowperm_inv = np.empty(m, np.int64)
+    rowperm_inv[mdl.basis_lu()[2]] = np.arange(m)
+    ctx.split_prepare(nonbasic_scale, rowperm_inv, np.nonzero(is_free)[0].astype(np.int64))
+    ctx.kktbasis_prepare(basic_var, colperm, np.where(is_free, 1.0, colscale[basic_var]))
+    a, b = rng.standard_normal(n + m), rng.standard_normal(m)
+    x, y, info = ctx.kktbasis_solve(a, b, 1e-13, 2000)
+    assert info["errflag"] == 0, info
+    A = AI.toarray()[:, keep]
+    K = np.block([[np.diag(g[keep]), A.T], [A, np.zeros((m, m))]])
+    sol = np.linalg.solve(K, np.concatenate([a[keep], b]))
+    x0 = np.zeros(n + m)
+    x0[keep] = sol[:keep.sum()]
+    y0 = sol[keep.sum():]
+    assert np.all(x[fixed] == 0.0)
+    assert rel_err(x, x0) <= 1e-8 and rel_err(y, y0) <= 1e-8
+    # the second block row holds to rounding (x_B = inverse(B)(b - N x_N), :179-193)
+    assert np.abs(AI @ x - b).max() <= 1e-10 * (1.0 + np.abs(x).max() * np.abs(AI).max())
+    assert info["time_B"] > 0 and info["time_NNt"] > 0
+    ctx.close()
+    mdl.close()

@@ -148,16 +148,31 @@ def run_operator_checks(name, lp, capi, oracle, pcr_iters=20, reps=10, log=print
     return out
 
 
-def run_basis_checks(name, lp, reflib, gpulib, log=print):
+def run_basis_checks(name, lp, reflib, gpulib, log=print, kkt_maxiter=200, volume_tol=2.0):
     """KKTSolverBasis path (config 3): reference build against the drop-in build on the same
     basis (same host LU provider), split operator apply, CR, and a full KKT solve."""
     out = {"config": name + "-basis", "m": lp.m, "n": lp.n, "nnz": int(lp.nnz)}
     t0 = time.time()
-    ref, gpu = reflib.model(lp, dualize=0), gpulib.model(lp, dualize=0)
+    # volume_tol: Maxvolume's threshold (reference src/maxvolume.cc:209); a large value keeps the
+    # host-side basis updates of KKTSolverBasis::Factorize out of a full-size timing run
+    params = dict(dualize=0, volume_tol=volume_tol)
+    ref, gpu = reflib.model(lp, **params), gpulib.model(lp, **params)
     out["model_s"] = time.time() - t0
     m, n = ref.m, ref.n
     rng = np.random.default_rng(11)
-    colscale = np.exp(rng.uniform(-3, 3, n + m))
+    # An interior iterate first: its scaling factors (reference src/iterate.cc:183-198) choose
+    # the basis, as in the IPM, so that KKTSolverBasis::Factorize below finds a basis that
+    # Maxvolume has little left to improve.
+    nm = n + m
+    _, _, lb, ub = ref.model_vectors()
+    has_lb, has_ub = np.isfinite(lb), np.isfinite(ub)
+    it = (rng.uniform(0.5, 1.5, nm), np.where(has_lb, np.exp(rng.uniform(-3, 3, nm)), np.inf),
+          np.where(has_ub, np.exp(rng.uniform(-3, 3, nm)), np.inf), rng.standard_normal(m),
+          np.where(has_lb, np.exp(rng.uniform(-3, 3, nm)), 0.0),
+          np.where(has_ub, np.exp(rng.uniform(-3, 3, nm)), 0.0))
+    with np.errstate(divide="ignore", invalid="ignore"):
+        g = np.where(has_lb, it[4] / it[1], 0.0) + np.where(has_ub, it[5] / it[2], 0.0)
+    colscale = np.where(g > 0, 1.0 / np.sqrt(np.maximum(g, 1e-300)), 1.0)
     for key, mdl in (("ref", ref), ("gpu", gpu)):
         t0 = time.time()
         mdl.basis_from_weights(colscale)
@@ -194,6 +209,37 @@ def run_basis_checks(name, lp, reflib, gpulib, log=print):
         assert abs(i0["iter"] - i1["iter"]) <= max(1, i0["iter"] // 20)
         out["cr_rel_err"] = rel_err(z1, z0)
         assert out["cr_rel_err"] <= 1e-5
+    # KKTSolverBasis: Factorize from an interior iterate (scaling factors, Maxvolume, LU,
+    # Prepare) and one full Solve per arm - right-hand side sweeps, SolveDense steps, CR, recovery
+    # (reference src/kkt_solver_basis.cc:20-194; on the device in the drop-in build).
+    a, b = rng.standard_normal(nm), rng.standard_normal(m)
+    sol = {}
+    for key, mdl in (("ref", ref), ("gpu", gpu)):
+        mdl.iterate_set(*it)
+        mdl.kktbasis_maxiter(kkt_maxiter)
+        t0 = time.time()
+        f = mdl.kktbasis_factorize()
+        out[f"kkt_factorize_{key}_s"] = time.time() - t0
+        assert f["err"] == 0, f
+        t0 = time.time()
+        x, y, info = mdl.kktbasis_solve(a, b, 1e-6)
+        out[f"kkt_solve_{key}_s"] = time.time() - t0
+        out[f"kkt_solve_{key}"] = {k: info[k] for k in ("err", "kktiter2", "time_cr2", "time_cr2_NNt",
+                                                        "time_cr2_B", "time_cr2_Bt")}
+        sol[key] = (x, y, info)
+    (x0, y0, i0), (x1, y1, i1) = sol["ref"], sol["gpu"]
+    assert i0["err"] == i1["err"], (i0, i1)
+    if i0["err"] == 0:
+        assert abs(i0["kktiter2"] - i1["kktiter2"]) <= max(1, int(i0["kktiter2"]) // 20)
+        out["kkt_x_rel_err"] = rel_err(x1, x0)
+        out["kkt_y_rel_err"] = rel_err(y1, y0)
+        assert out["kkt_x_rel_err"] <= 1e-4 and out["kkt_y_rel_err"] <= 1e-4
+    else:
+        # iteration limit on both arms: the iterates after kkt_maxiter CR steps
+        assert i0["kktiter2"] == i1["kktiter2"]
+        out["kkt_x_rel_err"] = rel_err(x1, x0)
+        out["kkt_y_rel_err"] = rel_err(y1, y0)
+        assert out["kkt_x_rel_err"] <= 1e-2 and out["kkt_y_rel_err"] <= 1e-2
     ref.close()
     gpu.close()
     log(json.dumps(out))
@@ -205,6 +251,8 @@ def main():
     ap.add_argument("configs", nargs="*", default=[])
     ap.add_argument("--basis", nargs="*", default=[])
     ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--volume-tol", type=float, default=2.0)
+    ap.add_argument("--kkt-maxiter", type=int, default=200)
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     if not args.configs and not args.basis:
@@ -224,7 +272,8 @@ def main():
     for name in args.basis:
         lp = make_lp(name, args.scale)
         results.append(run_basis_checks(name, lp, ipxlib.IpxLibrary(ipxlib.REF_LIB),
-                                        ipxlib.IpxLibrary(ipxlib.GPU_LIB)))
+                                        ipxlib.IpxLibrary(ipxlib.GPU_LIB),
+                                        kkt_maxiter=args.kkt_maxiter, volume_tol=args.volume_tol))
     if args.out:
         with open(args.out, "w") as f:
             json.dump(results, f, indent=1)

@@ -38,6 +38,7 @@ ap.add_argument("--switchiter", type=int, default=-1)
 ap.add_argument("--maxiter", type=int, default=300)
 ap.add_argument("--stop-at-switch", type=int, default=0,
                 help="-1: stop after the diagonal-preconditioned phase (reference debug parameter)")
+ap.add_argument("--debug", type=int, default=0, help="ipx debug level (1: per-iteration kktiter/step sizes in the log)")
 ap.add_argument("--out", default=None)
 args = ap.parse_args()
 
@@ -56,7 +57,8 @@ for impl, path in (("ref", ipxlib.REF_LIB), ("gpu", ipxlib.GPU_LIB)):
     s = lib.lp_solver()
     s.set_parameters(display=int(os.environ.get("IPX_DISPLAY", "0")), dualize=0,
                      crossover=args.crossover, switchiter=args.switchiter,
-                     ipm_maxiter=args.maxiter, stop_at_switch=args.stop_at_switch)
+                     ipm_maxiter=args.maxiter, stop_at_switch=args.stop_at_switch,
+                     debug=args.debug)
     assert s.load_model(lp) == 0
     t0 = time.perf_counter()
     s.solve()
