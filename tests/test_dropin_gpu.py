@@ -179,7 +179,9 @@ def test_kkt_solver_basis(pair):
         out.append(mdl.kktbasis_solve(a, b, 1e-8))
     (x0, y0, i0), (x1, y1, i1) = out
     assert i0["err"] == i1["err"] == 0
-    assert abs(i0["kktiter2"] - i1["kktiter2"]) <= 1
+    # several hundred CR iterations on the random LP: the count moves with the rounding of the
+    # right-hand side (the device forms inverse(B)(rhs - b) in one solve)
+    assert abs(i0["kktiter2"] - i1["kktiter2"]) <= max(1, int(i0["kktiter2"]) // 100)
     assert rel_err(y1, y0) <= 1e-6
     assert rel_err(x1, x0) <= 1e-6
 
@@ -205,7 +207,7 @@ def test_kkt_solver_basis_with_free_variables(pair):
         out.append(mdl.kktbasis_solve(a, b, 1e-9))
     (x0, y0, i0), (x1, y1, i1) = out
     assert i0["err"] == i1["err"] == 0
-    assert abs(i0["kktiter2"] - i1["kktiter2"]) <= 1
+    assert abs(i0["kktiter2"] - i1["kktiter2"]) <= max(1, int(i0["kktiter2"]) // 100)
     assert rel_err(y1, y0) <= 1e-6
     assert rel_err(x1, x0) <= 1e-6
 
