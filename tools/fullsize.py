@@ -244,11 +244,24 @@ def run_basis_checks(name, lp, reflib, gpulib, log=print, kkt_maxiter=200, volum
         out["kkt_y_rel_err"] = rel_err(y1, y0)
         assert out["kkt_x_rel_err"] <= 1e-4 and out["kkt_y_rel_err"] <= 1e-4
     else:
-        # iteration limit on both arms: the iterates after kkt_maxiter CR steps
+        # iteration limit on both arms
         assert i0["kktiter2"] == i1["kktiter2"]
         out["kkt_x_rel_err"] = rel_err(x1, x0)
         out["kkt_y_rel_err"] = rel_err(y1, y0)
-        assert out["kkt_x_rel_err"] <= 1e-2 and out["kkt_y_rel_err"] <= 1e-2
+    # What the KKT solver promises (reference src/kkt_solver.h:20-39), measured on both arms:
+    # the second block row AI x = b holds to rounding, the first block row a - G x - AI'y is
+    # what the CR tolerance (or its iteration limit) leaves. CR iterates of an ill-conditioned
+    # system part ways after a few dozen iterations, the residuals they reach do not.
+    import scipy.sparse as sp
+    AIp, AIi, AIx = ref.AI()
+    AI = sp.csc_matrix((AIx, AIi, AIp), shape=(m, nm))
+    gdiag = 1.0 / colscale ** 2
+    for key, (xs, ys, _) in sol.items():
+        out[f"kkt_res_primal_{key}"] = float(np.abs(AI @ xs - b).max() / (1.0 + np.abs(b).max()))
+        out[f"kkt_res_dual_{key}"] = float(np.abs(a - gdiag * xs - AI.T @ ys).max() /
+                                           (1.0 + np.abs(a).max()))
+    assert out["kkt_res_primal_gpu"] <= max(1e-9, 10.0 * out["kkt_res_primal_ref"]), out
+    assert out["kkt_res_dual_gpu"] <= max(1e-9, 10.0 * out["kkt_res_dual_ref"]), out
     ref.close()
     gpu.close()
     log(json.dumps(out))
