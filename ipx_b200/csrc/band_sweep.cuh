@@ -32,6 +32,8 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdlib>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -631,35 +633,130 @@ inline bool band_build(const BandPlan& P, const int* ptr, const int* idx, const 
             }
         });
     }
-    // pass 2: deal the runs of every (tile, warp) to the 32 lanes, longest
-    // first, each to the least loaded lane (ties: lowest lane), so loads differ
-    // by <= 1 whenever there are enough short runs. place[r] = lane << 16 | offset.
+    // pass 2: deal the runs of every (tile, warp) to the 32 lanes. place[r] = lane << 16 | offset.
+    //
+    // Runs longer than one entry go first, longest first, each to the least loaded lane (ties:
+    // lowest lane), so loads differ by <= 1 whenever there are enough short runs. The single
+    // entries - nine out of ten on a matrix without structure - then fill the rows one by one,
+    // and which entry goes to which lane is chosen by shared-memory bank: the kernel gathers
+    // v[index] (LDS.64) and adds into acc[segment] (LDS.64 + STS.64) once per entry, a 64-bit
+    // access of a warp is served half-warp by half-warp, and a half-warp takes as many wavefronts
+    // as its most loaded bank pair (index mod 16, segment mod 16). Dealt at random that is ~2.9
+    // and ~1.8 per access (13 wavefronts per row, measured: tools/band_conflicts.cu, ncu); here
+    // every half-row gets 16 entries with distinct gather banks and, where the pool allows,
+    // distinct accumulator banks. (bank_aware = false keeps the plain dealing for comparison.)
     std::vector<uint32_t> place(runs.size());
     std::vector<int> trows(ntw, 0);  // rows of (tile, warp)
+    const bool bank_aware = [] {
+        const char* env = std::getenv("IPXGPU_BAND_DEAL");
+        return !(env && std::string(env) == "plain");
+    }();
     band_parallel_for(ntw, nthreads, [&](size_t t_begin, size_t t_end) {
         std::vector<long long> order;
         std::vector<int> bucket_start;
+        std::vector<long long> pool[16];       // single entries by gather bank pair
+        std::vector<uint16_t> used_g, used_a;  // per (row, half): bank pairs taken
         for (size_t t = t_begin; t < t_end; t++) {
             const long long r0 = tcount[t], r1 = tcount[t + 1];
             const int nr = (int)(r1 - r0);
             if (nr == 0) continue;
+            const int vb = (int)((t / NW) % NVB);
             int maxlen = 0;
-            for (long long r = r0; r < r1; r++) maxlen = std::max(maxlen, (int)runs[r].len);
-            bucket_start.assign(maxlen + 2, 0);
-            for (long long r = r0; r < r1; r++) bucket_start[maxlen - runs[r].len + 1]++;
-            for (int b = 0; b <= maxlen; b++) bucket_start[b + 1] += bucket_start[b];
-            order.resize(nr);
-            for (long long r = r0; r < r1; r++)
-                order[bucket_start[maxlen - runs[r].len]++] = r;
+            long long total = 0;
+            for (long long r = r0; r < r1; r++) {
+                maxlen = std::max(maxlen, (int)runs[r].len);
+                total += runs[r].len;
+            }
             int load[32];
             for (int l = 0; l < 32; l++) load[l] = 0;
-            for (int k = 0; k < nr; k++) {
-                const long long r = order[k];
-                int best = 0;
-                for (int l = 1; l < 32; l++)
-                    if (load[l] < load[best]) best = l;
-                place[r] = ((uint32_t)best << 16) | (uint32_t)load[best];
-                load[best] += runs[r].len;
+            {
+                bucket_start.assign(maxlen + 2, 0);
+                for (long long r = r0; r < r1; r++) bucket_start[maxlen - runs[r].len + 1]++;
+                for (int b = 0; b <= maxlen; b++) bucket_start[b + 1] += bucket_start[b];
+                order.resize(nr);
+                for (long long r = r0; r < r1; r++)
+                    order[bucket_start[maxlen - runs[r].len]++] = r;
+            }
+            if (!bank_aware) {
+                for (int k = 0; k < nr; k++) {
+                    const long long r = order[k];
+                    int best = 0;
+                    for (int l = 1; l < 32; l++)
+                        if (load[l] < load[best]) best = l;
+                    place[r] = ((uint32_t)best << 16) | (uint32_t)load[best];
+                    load[best] += runs[r].len;
+                }
+            } else {
+                // Row by row, every lane that is free takes a new run: the longest one in the
+                // pool (buckets by the gather bank of the run's first entry, longest at the
+                // back) whose entries find their gather banks free in the rows it will occupy
+                // and whose accumulator bank is free in the row where it ends.
+                const int cap = (int)((total + 31) / 32) + 2 * maxlen + 2;
+                used_g.assign((size_t)cap * 2, 0);
+                used_a.assign((size_t)cap * 2, 0);
+                for (int b = 0; b < 16; b++) pool[b].clear();
+                for (int k = nr - 1; k >= 0; k--) {  // order[] is longest first
+                    const long long r = order[k];
+                    pool[(idx[runs[r].first] - vb * VB) & 15].push_back(r);
+                }
+                auto fits = [&](long long r, int half, int row) {
+                    const Run& R = runs[r];
+                    if (row + R.len > cap) return false;
+                    for (int j = 0; j < R.len; j++)
+                        if (used_g[(size_t)(row + j) * 2 + half] &
+                            (1u << ((idx[R.first + j] - vb * VB) & 15)))
+                            return false;
+                    return !(used_a[(size_t)(row + R.len - 1) * 2 + half] & (1u << (R.seg & 15)));
+                };
+                long long left = nr;
+                for (int row = 0; left > 0; row++) {
+                    for (int l = 0; l < 32 && left > 0; l++) {
+                        if (load[l] != row) continue;
+                        const int half = l >> 4;
+                        int bb = -1, bpos = -1, blen = 0;
+                        size_t bsize = 0;
+                        int fb = -1, flen = 0;  // fallback: longest run at the back of a bucket
+                        for (int b = 0; b < 16; b++) {
+                            const size_t sz = pool[b].size();
+                            if (sz == 0) continue;
+                            const int backlen = runs[pool[b][sz - 1]].len;
+                            if (backlen > flen) {
+                                flen = backlen;
+                                fb = b;
+                            }
+                            const int look = (int)std::min<size_t>(sz, 10);
+                            for (int q = 0; q < look; q++) {
+                                const long long r = pool[b][sz - 1 - q];
+                                const int len = runs[r].len;
+                                if (len < blen || (len == blen && sz <= bsize)) break;
+                                if (fits(r, half, row)) {
+                                    bb = b;
+                                    bpos = (int)(sz - 1 - q);
+                                    blen = len;
+                                    bsize = sz;
+                                    break;
+                                }
+                            }
+                        }
+                        int b = bb, pos = bpos;
+                        if (b < 0) {
+                            b = fb;
+                            pos = (int)pool[b].size() - 1;
+                        }
+                        const long long r = pool[b][pos];
+                        pool[b].erase(pool[b].begin() + pos);  // keeps the bucket sorted by length
+                        left--;
+                        const Run& R = runs[r];
+                        place[r] = ((uint32_t)l << 16) | (uint32_t)row;
+                        for (int j = 0; j < R.len && row + j < cap; j++)
+                            used_g[(size_t)(row + j) * 2 + half] |=
+                                (uint16_t)(1u << ((idx[R.first + j] - vb * VB) & 15));
+                        if (row + R.len - 1 < cap)
+                            used_a[(size_t)(row + R.len - 1) * 2 + half] |=
+                                (uint16_t)(1u << (R.seg & 15));
+                        load[l] = row + R.len;
+                    }
+                }
             }
             int mx = 0;
             for (int l = 0; l < 32; l++) mx = std::max(mx, load[l]);
