@@ -94,6 +94,17 @@ struct BandArgs {
     int slot;
 };
 
+// Readiness of the gathered vector, piece by piece (persistent CR kernel): piece f = gather
+// indices [f * div, (f+1) * div) may be staged once flags[f] has reached gen. The producer lane
+// waits for the pieces a band overlaps before it issues the band's bulk copies, so the sweep
+// that writes the vector and the sweep that gathers from it need no grid barrier between them.
+struct BandReady {
+    const unsigned* flags = nullptr;  // nullptr: the whole vector is ready
+    unsigned gen = 0;
+    int div = 1;
+    int nflags = 0;
+};
+
 // ---- PTX helpers (mbarrier + bulk copy) ----
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) {
@@ -179,7 +190,8 @@ __device__ __forceinline__ double band_ld_f64(const void* p) {
 // aligned). The shared memory may be reused as soon as the call returns.
 template <int NW, int D, int DBG = 0, int LD = 0>
 __device__ __forceinline__ double band_sweep_item(const BandDev& T, const BandArgs& A, int mode,
-                                                  int item, unsigned char* smem_raw) {
+                                                  int item, unsigned char* smem_raw,
+                                                  const BandReady& ready = BandReady()) {
     const BandPlan& P = T.plan;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NBUF = P.NBUF;
@@ -207,6 +219,22 @@ __device__ __forceinline__ double band_sweep_item(const BandDev& T, const BandAr
         if (r >= nk) r -= nk;
         const int vbase = (vb0 + r) * P.VB;
         const int vlen = min(P.VB, P.V - vbase);
+        if (ready.flags != nullptr) {
+            const int f1 = min(ready.nflags - 1, (vbase + vlen - 1) / ready.div);
+            for (int f = vbase / ready.div; f <= f1; f++) {
+                unsigned now;
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];"
+                                 : "=r"(now)
+                                 : "l"(ready.flags + f)
+                                 : "memory");
+                } while ((int)(now - ready.gen) < 0);
+            }
+            // what the pieces' writers stored (generic proxy) must be seen by this thread's
+            // loads (no stale L1 line) and by the bulk copies
+            __threadfence();
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
         double* dst = v_buf + (size_t)b * P.VB;
         const unsigned bytes = (unsigned)(vlen & ~1) * 8u;
         if (vlen & 1) dst[vlen - 1] = A.v[vbase + vlen - 1];

@@ -181,6 +181,7 @@ struct ipxgpu_ctx {
     // persistent CR kernel (pcr_fused.cuh): grid barrier words and per-CTA partials
     unsigned* fused_bar = nullptr;
     unsigned* fused_tickets = nullptr;  // per row block of sweep 2
+    unsigned* fused_flags = nullptr;    // readiness flags: [sweep-1 items | CTAs]
     double* fused_red = nullptr;
     int fused_grid = 0;
 

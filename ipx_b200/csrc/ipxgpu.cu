@@ -353,6 +353,9 @@ static int run_cr_fused(ipxgpu_ctx* c, bool precond, bool zero_start, bool use_r
         IPXGPU_TRY(dev_alloc(&c->fused_bar, 1));
         IPXGPU_TRY(dev_alloc(&c->fused_tickets, (size_t)c->band2->plan.NSB));
         IPXGPU_TRY(dev_alloc(&c->fused_red, (size_t)kFusedStages * 3 * c->fused_grid + 1));
+        IPXGPU_TRY(dev_alloc(&c->fused_flags, (size_t)c->band1->plan.nitems + c->fused_grid));
+        if (c->fused_grid > kMaxGridSync)
+            return fail(IPXGPU_ERR_UNSUPPORTED, "persistent CR kernel: more SMs than kMaxGridSync");
     }
     if (!c->band2->partials)
         IPXGPU_TRY(dev_alloc(&c->band2->partials, (size_t)c->band2->plan.nparts * m));
@@ -375,6 +378,9 @@ static int run_cr_fused(ipxgpu_ctx* c, bool precond, bool zero_start, bool use_r
                                 sizeof(double), c->stream));
     IPXGPU_CUDA(cudaMemsetAsync(c->fused_bar, 0, sizeof(unsigned), c->stream));
     IPXGPU_CUDA(cudaMemsetAsync(c->fused_tickets, 0, sizeof(unsigned) * c->band2->plan.NSB,
+                                c->stream));
+    IPXGPU_CUDA(cudaMemsetAsync(c->fused_flags, 0,
+                                sizeof(unsigned) * ((size_t)c->band1->plan.nitems + c->fused_grid),
                                 c->stream));
     if (zero_start) IPXGPU_CUDA(cudaMemsetAsync(c->v_y, 0, sizeof(double) * m, c->stream));
 
@@ -410,6 +416,13 @@ static int run_cr_fused(ipxgpu_ctx* c, bool precond, bool zero_start, bool use_r
     F.sync = GridSync{c->fused_bar, c->fused_red};
     F.abort_word = c->fused_red + (size_t)kFusedStages * 3 * c->fused_grid;
     F.block_tickets = c->fused_tickets;
+    {
+        // IPXGPU_FUSED_FLAGS=0: grid barriers between the stages instead of readiness flags
+        const char* env = std::getenv("IPXGPU_FUSED_FLAGS");
+        const bool flags = !(env && std::atoi(env) == 0);
+        F.t_ready = flags ? c->fused_flags : nullptr;
+        F.x_ready = flags ? c->fused_flags + c->band1->plan.nitems : nullptr;
+    }
     F.st = c->st_dev;
     F.abort_flag = &c->mirror_dev->abort;
     F.trace = nullptr;
@@ -748,6 +761,7 @@ void ipxgpu_destroy(ipxgpu_ctx* c) {
     dev_free(c->xchg_abort);
     dev_free(c->tri_err);
     dev_free(c->fused_tickets);
+    dev_free(c->fused_flags);
     dev_free(c->fused_red);
     if (c->band1) { free_band(c->band1); delete c->band1; }
     if (c->band2) { free_band(c->band2); delete c->band2; }

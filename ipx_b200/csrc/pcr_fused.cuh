@@ -50,6 +50,11 @@ struct FusedArgs {
     GridSync sync;
     double* abort_word; // set nonzero by CTA 0 when the host asked to stop
     unsigned* block_tickets;  // [T2.plan.NSB], zero before the launch: items done per row block
+    // Readiness flags, zero before the launch (nullptr: grid barriers instead). t_ready[i]: the
+    // number of applies whose sweep-1 item i has written its block of t; x_ready[c]: the number
+    // of updates after which CTA c's slice of the vector the next apply gathers is final.
+    unsigned* t_ready;
+    unsigned* x_ready;
     CrState* st;
     const volatile int* abort_flag;  // host-mapped; nonzero asks the solve to stop
     unsigned long long* trace;       // tuning only: globaltimer of CTA 0 at every stage end
@@ -87,6 +92,7 @@ __device__ __forceinline__ bool xll_load(const ulonglong2* p, unsigned gen, doub
 }
 
 constexpr int kFusedStages = 6;
+constexpr int kMaxGridSync = 256;  // CTAs of the persistent kernel (one per SM)
 enum FusedStage : int { kStSweep1 = 0, kStSweep2, kStCombine, kStInit, kStDirection, kStUpdate };
 
 __device__ __forceinline__ void fence_proxy_async() {
@@ -126,13 +132,18 @@ __device__ __forceinline__ void grid_sync(const GridSync& g, unsigned gen, int s
     }
     __syncthreads();
     if (stage >= 0) {
+        // Every CTA reduces the published values in CTA order (identical results everywhere).
+        // The loads go out together (one thread per value), the sums run in a fixed order.
+        const double* base = g.vals + (size_t)stage * 3 * nblk;
+        double* s_vals = s_bcast + 4;  // [3 * kMaxGridSync]
+        for (int q = threadIdx.x; q < 3 * nblk; q += blockDim.x) s_vals[q] = __ldcg(base + q);
+        __syncthreads();
         if (threadIdx.x < 32) {
-            const double* base = g.vals + (size_t)stage * 3 * nblk;
             double s = 0.0, s2 = 0.0, mx = 0.0;
             for (int b = threadIdx.x; b < nblk; b += 32) {
-                s += __ldcg(base + b);
-                s2 += __ldcg(base + nblk + b);
-                mx = fmax(mx, __ldcg(base + 2 * nblk + b));
+                s += s_vals[b];
+                s2 += s_vals[nblk + b];
+                mx = fmax(mx, s_vals[2 * nblk + b]);
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -186,7 +197,7 @@ __global__ void __launch_bounds__((NW + 1) * 32, 1)
 pcr_fused_kernel(FusedArgs F) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double s_red[96];
-    __shared__ double s_bcast[4];
+    __shared__ double s_bcast[4 + 3 * kMaxGridSync];
     __shared__ CrState s_st;   // this CTA's replica of the solve state
 
     const int tid = threadIdx.x;
@@ -228,13 +239,47 @@ pcr_fused_kernel(FusedArgs F) {
         trace();
     };
 
-    // lhs (own m-slice) = A W A' x; returns the total x'lhs to all threads.
-    auto apply = [&](const double* x, double* lhs) -> double {
+    // With readiness flags (single shard, sweep 2 folded) a CTA goes from one stage to the next
+    // as soon as the pieces IT needs are there: sweep 1 waits per band of x for the slices of
+    // the CTAs that updated it, sweep 2 per band of t for the sweep-1 items that wrote it. A CTA
+    // that is ahead no longer waits for the slowest one at two of the four grid barriers of an
+    // iteration (the SMs' streaming rates differ by 10-15 %), it starts its next item instead.
+    const bool flags_on = F.t_ready != nullptr && F.nranks == 1 &&
+                          F.T2.plan.nitems <= (int)gridDim.x;
+    unsigned x_gen = 0;  // updates so far (identical in all CTAs)
+
+    // lhs (own m-slice) = A W A' x; returns the total x'lhs to all threads. x_flagged: x was
+    // written by the update stage and is guarded by x_ready (no grid barrier since);
+    // extra_max: rides the reduction that ends the apply (the update's residual norm).
+    auto apply = [&](const double* x, double* lhs, bool x_flagged, double extra_max) -> double {
         BandArgs a1{x, F.Wc, nullptr, nullptr, F.t, kApplyPlain, kSlotNone};
-        for (int item = blockIdx.x; item < F.T1.plan.nitems; item += gridDim.x)
-            band_sweep_item<NW, D, DBG>(F.T1, a1, kBandColScale, item, smem_raw);
-        sync_plain();
+        BandReady rx;
+        if (flags_on && x_flagged) {
+            rx.flags = F.x_ready;
+            rx.gen = x_gen;
+            rx.div = chunk;
+            rx.nflags = (int)gridDim.x;
+        }
+        for (int item = blockIdx.x; item < F.T1.plan.nitems; item += gridDim.x) {
+            band_sweep_item<NW, D, DBG>(F.T1, a1, kBandColScale, item, smem_raw, rx);
+            if (flags_on && tid == 0) {
+                // this item's block of t is written (the item ends with a CTA barrier)
+                fence_proxy_async();
+                __threadfence();
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(F.t_ready + item),
+                             "r"((unsigned)(s_applies + 1))
+                             : "memory");
+            }
+        }
+        if (!flags_on) sync_plain();
         BandArgs a2{F.t, nullptr, nullptr, nullptr, nullptr, kApplyPlain, kSlotNone};
+        BandReady rt;
+        if (flags_on) {
+            rt.flags = F.t_ready;
+            rt.gen = (unsigned)(s_applies + 1);
+            rt.div = F.T1.plan.SB;
+            rt.nflags = F.T1.plan.nitems;
+        }
         const int nparts = F.T2.plan.nparts;
         double dot = 0.0;
         if (F.nranks == 1 && F.T2.plan.nitems <= (int)gridDim.x) {
@@ -245,7 +290,7 @@ pcr_fused_kernel(FusedArgs F) {
             ++s_applies;
             if ((int)blockIdx.x < F.T2.plan.nitems) {
                 const int item = blockIdx.x;
-                band_sweep_item<NW, D, DBG>(F.T2, a2, kBandPartial, item, smem_raw);
+                band_sweep_item<NW, D, DBG>(F.T2, a2, kBandPartial, item, smem_raw, rt);
                 const int sb = item / nparts, part = item - sb * nparts;
                 if (tid == 0) {
                     __threadfence();
@@ -466,14 +511,14 @@ pcr_fused_kernel(FusedArgs F) {
                 dot += __dmul_rn(x[i], yv);
             }
         }
-        sync_stage(kStCombine, dot, 0.0, 0.0);
+        sync_stage(kStCombine, dot, 0.0, extra_max);
         stamp_lead(kSlotOp);
         return r0;
     };
 
     // ---- initialisation (reference :33-40, :118-127) ----
     if (!F.zero_start) {
-        apply(v.y, v.Cs);  // own slice of C*y, read back by the same threads below
+        apply(v.y, v.Cs, false, 0.0);  // own slice of C*y, read back by the same threads below
     }
     {
         double rs = 0.0, mx = 0.0;
@@ -500,7 +545,7 @@ pcr_fused_kernel(FusedArgs F) {
     }
     const double* sv = precond ? v.s : v.r;
     {
-        const double dot = apply(sv, v.Cs);
+        const double dot = apply(sv, v.Cs, false, 0.0);
         if (tid == 0) {
             s_st.cdot = dot;
             s_st.beta = 0.0;
@@ -582,6 +627,7 @@ pcr_fused_kernel(FusedArgs F) {
         if (s_st.done) break;
 
         // ---- update (reference :72-73 / :173-175) ----
+        double upd_max = 0.0;
         {
             const double alpha = s_st.alpha;
             double mx = 0.0;
@@ -593,13 +639,29 @@ pcr_fused_kernel(FusedArgs F) {
                 const double sc = v.resscale ? __dmul_rn(v.resscale[i], ri) : ri;
                 mx = fmax(mx, fabs(sc));
             }
-            sync_stage(kStUpdate, 0.0, 0.0, mx);
-            if (tid == 0) s_st.resnorm = r2;
+            ++x_gen;
+            if (flags_on) {
+                // no grid barrier: publish this CTA's slice, the residual norm rides the
+                // reduction at the end of the apply
+                __syncthreads();
+                if (tid == 0) {
+                    fence_proxy_async();
+                    __threadfence();
+                    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(F.x_ready + blockIdx.x),
+                                 "r"(x_gen)
+                                 : "memory");
+                }
+                upd_max = mx;
+            } else {
+                sync_stage(kStUpdate, 0.0, 0.0, mx);
+                if (tid == 0) s_st.resnorm = r2;
+            }
             stamp_lead(kSlotVec);
         }
         // ---- C.Apply and its scalar step (reference :75-81 / :176-184) ----
         {
-            const double dot = apply(sv, v.Cs);
+            const double dot = apply(sv, v.Cs, true, flags_on ? upd_max : 0.0);
+            if (flags_on && tid == 0) s_st.resnorm = r2;
             if (tid == 0) {
                 s_st.beta = dot / s_st.cdot;
                 s_st.cdot = dot;
