@@ -150,6 +150,24 @@ int ipxgpu_diag_set(ipxgpu_ctx* ctx, const double* diag);
 int ipxgpu_diag_apply(ipxgpu_ctx* ctx, const double* rhs, double* lhs,
                       double* rhs_dot_lhs);
 
+/* Dense-column part of the preconditioner (reference src/diagonal_precond.cc:48-102
+ * Factorize, :133-149 _Apply; at most 1000 columns, src/model.cc:34-56).
+ *
+ * ipxgpu_diag_factorize_masked: the diagonal E of AI*W*AI' WITHOUT the nd columns listed in
+ * dense_cols (ascending, structural) - built directly with their weights zeroed, so nothing
+ * is subtracted afterwards (:28-36 never adds them). W / use_prepared as above.
+ * ipxgpu_smw_load: installs Ad = AI[:, dense_cols] (CSC: Adp[nd+1], Adi, Adx, rows ascending
+ * per column) and the Cholesky factor L (nd x nd, column-major, lower triangle, as dpotrf
+ * 'L' leaves it) of the Schur complement S = inv(Wd) + Ad' inv(E) Ad. From then on
+ * ipxgpu_diag_apply and the preconditioned CR solves apply
+ * inv(E) - inv(E) Ad inv(S) Ad' inv(E) entirely on the device.
+ * ipxgpu_smw_clear: back to the pure diagonal (also done by ipxgpu_diag_factorize). */
+int ipxgpu_diag_factorize_masked(ipxgpu_ctx* ctx, const double* W, int use_prepared,
+                                 int64_t nd, const int64_t* dense_cols);
+int ipxgpu_smw_load(ipxgpu_ctx* ctx, int64_t nd, const int64_t* Adp, const int64_t* Adi,
+                    const double* Adx, const double* L);
+int ipxgpu_smw_clear(ipxgpu_ctx* ctx);
+
 /* ---- ConjugateResiduals (reference src/conjugate_residuals.h) ---- */
 
 typedef struct ipxgpu_cr_result {

@@ -38,6 +38,7 @@ EXPORTS = ("ipxgpu_default_options ipxgpu_last_error ipxgpu_device_count ipxgpu_
            "ipxgpu_destroy ipxgpu_get_layout ipxgpu_get_tiling ipxgpu_synchronize ipxgpu_partition_columns ipxgpu_comm_unique_id "
            "ipxgpu_comm_init ipxgpu_normal_prepare ipxgpu_normal_prepare_dev ipxgpu_normal_apply "
            "ipxgpu_normal_apply_dev ipxgpu_diag_factorize ipxgpu_diag_get ipxgpu_diag_set "
+           "ipxgpu_diag_factorize_masked ipxgpu_smw_load ipxgpu_smw_clear "
            "ipxgpu_diag_apply ipxgpu_pcr_solve ipxgpu_pcr_solve_dev ipxgpu_cr_solve ipxgpu_kktdiag_factorize "
            "ipxgpu_kktdiag_solve ipxgpu_lu_load ipxgpu_tri_solve ipxgpu_split_prepare "
            "ipxgpu_split_apply ipxgpu_kktbasis_prepare ipxgpu_basis_solve ipxgpu_kktbasis_solve ipxgpu_time_normal_apply ipxgpu_launch_count ipxgpu_band_selftest ipxgpu_peer_export ipxgpu_peer_import").split()
@@ -218,6 +219,24 @@ class Context:
         rhs, lhs, dot = _f64(rhs), np.empty(self.m), C.c_double(np.nan)
         _check(self.lib.ipxgpu_diag_apply(self.h, _d(rhs), _d(lhs), C.byref(dot)))
         return lhs, dot.value
+
+    def diag_factorize_masked(self, W, dense_cols, use_prepared=False):
+        W, cols = _f64(W), _i64(dense_cols)
+        _check(self.lib.ipxgpu_diag_factorize_masked(self.h, _d(W), C.c_int(1 if use_prepared else 0),
+                                                     C.c_int64(len(cols)), _i(cols)))
+
+    def smw_load(self, Adp, Adi, Adx, L):
+        """Ad (CSC of the dense columns) and the lower Cholesky factor L (nd x nd, column-major)
+        of the Schur complement; switches the preconditioner to its SMW form."""
+        Adp, Adi, Adx = _i64(Adp), _i64(Adi), _f64(Adx)
+        L = np.asfortranarray(L, dtype=np.float64)
+        nd = len(Adp) - 1
+        assert L.shape == (nd, nd)
+        _check(self.lib.ipxgpu_smw_load(self.h, C.c_int64(nd), _i(Adp), _i(Adi), _d(Adx),
+                                        L.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def smw_clear(self):
+        _check(self.lib.ipxgpu_smw_clear(self.h))
 
     # ---- ConjugateResiduals ----
     def _cr(self, fn, pre_args, rhs, tol, resscale, maxiter, lhs0, hist_cap, interrupt):

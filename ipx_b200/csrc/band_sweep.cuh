@@ -213,23 +213,37 @@ __device__ __forceinline__ double band_sweep_item(const BandDev& T, const BandAr
     const int nk = min(P.NVB, vb0 + P.K) - vb0;
     const int rot = sb % nk;
 
-    // Stages band k of the item into ring buffer b (producer lane only).
-    auto stage_band = [&](int k, int b, uint64_t keep) {
+    // Band k of the item: first gather index and length.
+    auto band_range = [&](int k, int* vbase, int* vlen) {
         int r = k + rot;
         if (r >= nk) r -= nk;
-        const int vbase = (vb0 + r) * P.VB;
-        const int vlen = min(P.VB, P.V - vbase);
+        *vbase = (vb0 + r) * P.VB;
+        *vlen = min(P.VB, P.V - *vbase);
+    };
+    // Whole producer warp: waits until the pieces band k overlaps are ready. Every lane polls
+    // its own flags (a band overlaps up to a dozen pieces; one lane polling them one after the
+    // other costs an L2 round trip per piece).
+    auto wait_ready = [&](int k) {
+        if (ready.flags == nullptr) return;
+        int vbase, vlen;
+        band_range(k, &vbase, &vlen);
+        const int f1 = min(ready.nflags - 1, (vbase + vlen - 1) / ready.div);
+        for (int f = vbase / ready.div + lane; f <= f1; f += 32) {
+            unsigned now;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];"
+                             : "=r"(now)
+                             : "l"(ready.flags + f)
+                             : "memory");
+            } while ((int)(now - ready.gen) < 0);
+        }
+        __syncwarp();
+    };
+    // Stages band k of the item into ring buffer b (producer lane only, after wait_ready).
+    auto stage_band = [&](int k, int b, uint64_t keep) {
+        int vbase, vlen;
+        band_range(k, &vbase, &vlen);
         if (ready.flags != nullptr) {
-            const int f1 = min(ready.nflags - 1, (vbase + vlen - 1) / ready.div);
-            for (int f = vbase / ready.div; f <= f1; f++) {
-                unsigned now;
-                do {
-                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];"
-                                 : "=r"(now)
-                                 : "l"(ready.flags + f)
-                                 : "memory");
-                } while ((int)(now - ready.gen) < 0);
-            }
             // what the pieces' writers stored (generic proxy) must be seen by this thread's
             // loads (no stale L1 line) and by the bulk copies
             __threadfence();
@@ -246,49 +260,56 @@ __device__ __forceinline__ double band_sweep_item(const BandDev& T, const BandAr
                      reinterpret_cast<const unsigned char*>(A.v + vbase) + off, n, full + b, keep);
         }
     };
-    const bool producer = tid == NW * 32;
     uint64_t keep = 0;
-    if (producer) {
-        // The producer lane sets up the barriers and starts the first NBUF bands
-        // at once, while the other threads clear the accumulators and fetch the
-        // row table: the first band is (nearly) there when the consumers start.
-        for (int b = 0; b < NBUF; b++) {
-            mbar_init(full + b, 1);
-            mbar_init(empty + b, NW);
+    if (warp == NW) {
+        // The producer warp sets up the barriers and starts the first NBUF bands at once,
+        // while the other threads clear the accumulators and fetch the row table: the first
+        // band is (nearly) there when the consumers start.
+        if (lane == 0) {
+            for (int b = 0; b < NBUF; b++) {
+                mbar_init(full + b, 1);
+                mbar_init(empty + b, NW);
+            }
+            mbar_fence_init();
+            keep = policy_evict_last();
         }
-        mbar_fence_init();
-        keep = policy_evict_last();
         if (!(DBG & 1))
-            for (int k = 0; k < NBUF && k < nk; k++) stage_band(k, k, keep);
+            for (int k = 0; k < NBUF && k < nk; k++) {
+                wait_ready(k);
+                if (lane == 0) stage_band(k, k, keep);
+            }
     } else {
-        const int ptid = tid < NW * 32 ? tid : tid - 1;  // the other 32*(NW+1) - 1 threads
-        const int pcount = (NW + 1) * 32 - 1;
-        for (int s = ptid; s <= nseg; s += pcount) acc_s[s] = 0.0;
+        const int pcount = NW * 32;
+        for (int s = tid; s <= nseg; s += pcount) acc_s[s] = 0.0;
         const int* src = T.row_ptr + (size_t)item * NW * (P.K + 1);
-        for (int i = ptid; i < NW * (P.K + 1); i += pcount) s_rows[i] = src[i];
+        for (int i = tid; i < NW * (P.K + 1); i += pcount) s_rows[i] = src[i];
     }
     __syncthreads();
     if ((DBG & 4) && tid == 0) trace[1] = globaltimer();
 
     if (warp == NW) {
         // ===== producer: stage the remaining bands as buffers are released =====
-        if (lane == 0 && !(DBG & 1)) {
+        if (lane > 0 && mode == kBandColScale && A.W != nullptr) {
+            // pull the weights of the epilogue into L2 meanwhile
+            const char* wbase = reinterpret_cast<const char*>(A.W + seg_base);
+            const long long wbytes = (long long)nseg * 8;
+            for (long long o = (long long)(lane - 1) * 128; o < wbytes; o += 31 * 128)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(wbase + o));
+        }
+        if (!(DBG & 1) && (lane == 0 || ready.flags != nullptr)) {
             int b = 0;
             unsigned par = 0;  // parity of the previous use of buffer b
             for (int k = NBUF; k < nk; k++) {
-                mbar_wait(empty + b, par);
-                stage_band(k, b, keep);
+                wait_ready(k);
+                if (lane == 0) {
+                    mbar_wait(empty + b, par);
+                    stage_band(k, b, keep);
+                }
                 if (++b == NBUF) {
                     b = 0;
                     par ^= 1u;
                 }
             }
-        } else if (lane > 0 && mode == kBandColScale && A.W != nullptr) {
-            // idle lanes: pull the weights of the epilogue into L2 meanwhile
-            const char* wbase = reinterpret_cast<const char*>(A.W + seg_base);
-            const long long wbytes = (long long)nseg * 8;
-            for (long long o = (long long)(lane - 1) * 128; o < wbytes; o += 31 * 128)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(wbase + o));
         }
     } else {
         // ===== consumers =====

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "smw.cuh"
 #include "../../include/ipxgpu.h"
 
 namespace ipxgpu {
@@ -138,6 +139,10 @@ struct ipxgpu_ctx {
     double* ybuf = nullptr;  // m+1
     double* diag = nullptr;  // m
     bool diag_ready = false;
+    // dense-column part of the preconditioner (smw.cuh); inactive: pure diagonal
+    ipxgpu::SmwDev smw;
+    bool smw_active = false;
+    double* W_mask = nullptr;  // nloc: structural weights with the dense columns zeroed
 
     // CR work vectors (allocated on first solve)
     double *v_y = nullptr, *v_r = nullptr, *v_s = nullptr, *v_p = nullptr, *v_Cp = nullptr,

@@ -16,6 +16,7 @@
 #pragma once
 
 #include "common.cuh"
+#include "smw.cuh"
 
 namespace ipxgpu {
 
@@ -91,45 +92,11 @@ cr_update_kernel(CrVectors v, Reduce red, CrState* st) {
     }
 }
 
-// Reference src/conjugate_residuals.cc:79-80 / :181-207 followed by the tests
-// at the top of the loop (:50-71 / :137-172), in the reference's order.
-__global__ void __launch_bounds__(kBlock)
-cr_direction_kernel(CrVectors v, Reduce red, CrState* st) {
-    __shared__ double s_red[kWarps];
-    __shared__ int s_flag;
-    if (st->done) return;
-    const double beta = st->beta;
-    const bool precond = st->precond != 0;
-    const long long iter = st->iter;
-    const bool recompute = precond && iter > 0 && (iter % 5 == 0);
-    const double* sv = precond ? v.s : v.r;
-    double pd = 0.0, rs = 0.0;
-    for (int i = blockIdx.x * kBlock + threadIdx.x; i < v.m; i += gridDim.x * kBlock) {
-        const double pn = sv[i] + __dmul_rn(beta, v.p[i]);
-        const double cpn = v.Cs[i] + __dmul_rn(beta, v.Cp[i]);
-        v.p[i] = pn;
-        v.Cp[i] = cpn;
-        if (precond) {
-            const double d = v.diag[i];
-            const double qi = cpn / d;
-            v.q[i] = qi;
-            pd += __dmul_rn(qi, cpn);
-            if (recompute) {
-                const double ri = v.r[i];
-                const double sn = ri / d;
-                v.s[i] = sn;
-                rs += __dmul_rn(sn, ri);
-            }
-        } else {
-            pd += __dmul_rn(cpn, cpn);
-        }
-    }
-    const double bpd = block_sum(pd, s_red);
-    const double brs = block_sum(rs, s_red);
-    double tpd, trs, tm;
-    if (!grid_reduce(red, bpd, brs, 0.0, s_red, &s_flag, &tpd, &trs, &tm)) return;
-    if (threadIdx.x != 0) return;
-
+// The monotonicity test of the recomputed preconditioned residual (reference
+// src/conjugate_residuals.cc:187-207) and the tests at the top of the loop (:50-71 / :137-172),
+// in the reference's order; alpha for the next pass. One thread, after the reductions.
+__device__ __forceinline__ void cr_direction_tests(CrState* st, bool precond, bool recompute,
+                                                   long long iter, double tpd, double trs) {
     int done = 0, err = 0;
     if (recompute) {  // :187-207
         if (trs >= st->rsdot_prev) {
@@ -167,6 +134,96 @@ cr_direction_kernel(CrVectors v, Reduce red, CrState* st) {
     st->done = done;
     stamp(st, precond ? kSlotPre : kSlotVec);
     publish(st);
+}
+
+// Reference src/conjugate_residuals.cc:79-80 / :181-207 followed by the tests
+// at the top of the loop (:50-71 / :137-172), in the reference's order.
+// vec_only: p and Cp only - the preconditioner has a dense-column part and is applied by the
+// kernels that follow (smw_gather, smw_solve, cr_direction_smw_kernel).
+__global__ void __launch_bounds__(kBlock)
+cr_direction_kernel(CrVectors v, Reduce red, CrState* st, int vec_only) {
+    __shared__ double s_red[kWarps];
+    __shared__ int s_flag;
+    if (st->done) return;
+    const double beta = st->beta;
+    const bool precond = st->precond != 0;
+    const long long iter = st->iter;
+    const bool recompute = precond && iter > 0 && (iter % 5 == 0);
+    const double* sv = precond ? v.s : v.r;
+    double pd = 0.0, rs = 0.0;
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < v.m; i += gridDim.x * kBlock) {
+        const double pn = sv[i] + __dmul_rn(beta, v.p[i]);
+        const double cpn = v.Cs[i] + __dmul_rn(beta, v.Cp[i]);
+        v.p[i] = pn;
+        v.Cp[i] = cpn;
+        if (vec_only) continue;
+        if (precond) {
+            const double d = v.diag[i];
+            const double qi = cpn / d;
+            v.q[i] = qi;
+            pd += __dmul_rn(qi, cpn);
+            if (recompute) {
+                const double ri = v.r[i];
+                const double sn = ri / d;
+                v.s[i] = sn;
+                rs += __dmul_rn(sn, ri);
+            }
+        } else {
+            pd += __dmul_rn(cpn, cpn);
+        }
+    }
+    if (vec_only) return;
+    const double bpd = block_sum(pd, s_red);
+    const double brs = block_sum(rs, s_red);
+    double tpd, trs, tm;
+    if (!grid_reduce(red, bpd, brs, 0.0, s_red, &s_flag, &tpd, &trs, &tm)) return;
+    if (threadIdx.x != 0) return;
+    cr_direction_tests(st, precond, recompute, iter, tpd, trs);
+}
+
+// Second half of the direction stage when the preconditioner has a dense-column part:
+// q = inv(P) Cp (and s = inv(P) r on recompute iterations) from the solved z, the two dots,
+// then the tests.
+__global__ void __launch_bounds__(kBlock)
+cr_direction_smw_kernel(CrVectors v, SmwDev S, Reduce red, CrState* st) {
+    __shared__ double s_red[kWarps];
+    __shared__ int s_flag;
+    if (st->done) return;
+    const long long iter = st->iter;
+    const bool recompute = iter > 0 && (iter % 5 == 0);
+    double pd = 0.0, rs = 0.0;
+    smw_rows(S, v.diag, v.Cp, v.r, recompute, [&](int i, double qi, double sn) {
+        v.q[i] = qi;
+        pd += __dmul_rn(qi, v.Cp[i]);
+        if (recompute) {
+            v.s[i] = sn;
+            rs += __dmul_rn(sn, v.r[i]);
+        }
+    });
+    const double bpd = block_sum(pd, s_red);
+    const double brs = block_sum(rs, s_red);
+    double tpd, trs, tm;
+    if (!grid_reduce(red, bpd, brs, 0.0, s_red, &s_flag, &tpd, &trs, &tm)) return;
+    if (threadIdx.x != 0) return;
+    cr_direction_tests(st, true, recompute, iter, tpd, trs);
+}
+
+// s = inv(P) r and r's' at the start of a solve (reference :124-125) for the same case.
+__global__ void __launch_bounds__(kBlock)
+cr_init_smw_kernel(CrVectors v, SmwDev S, Reduce red, CrState* st) {
+    __shared__ double s_red[kWarps];
+    __shared__ int s_flag;
+    double rs = 0.0;
+    smw_rows(S, v.diag, v.r, nullptr, false, [&](int i, double si, double) {
+        v.s[i] = si;
+        rs += __dmul_rn(si, v.r[i]);
+    });
+    const double bs = block_sum(rs, s_red);
+    double ts, ts2, tm;
+    if (grid_reduce(red, bs, 0.0, 0.0, s_red, &s_flag, &ts, &ts2, &tm) && threadIdx.x == 0) {
+        st->rsdot_prev = ts;
+        stamp(st, kSlotPre);
+    }
 }
 
 // After a sharded C.Apply the dot lives in Cs[m] only once the allreduce has

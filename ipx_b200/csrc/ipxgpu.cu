@@ -417,9 +417,12 @@ static int run_cr_fused(ipxgpu_ctx* c, bool precond, bool zero_start, bool use_r
     F.abort_word = c->fused_red + (size_t)kFusedStages * 3 * c->fused_grid;
     F.block_tickets = c->fused_tickets;
     {
-        // IPXGPU_FUSED_FLAGS=0: grid barriers between the stages instead of readiness flags
+        // IPXGPU_FUSED_FLAGS=1: per-piece readiness flags instead of two of the grid barriers
+        // of an iteration. Measured on B200 (C2): 82.1 us per apply with the flags against
+        // 70.7 us with the barriers - the producer's per-band polls and fences cost more than
+        // the 2 x 3 us of barrier they replace - so the barriers stay the default.
         const char* env = std::getenv("IPXGPU_FUSED_FLAGS");
-        const bool flags = !(env && std::atoi(env) == 0);
+        const bool flags = env && std::atoi(env) != 0;
         F.t_ready = flags ? c->fused_flags : nullptr;
         F.x_ready = flags ? c->fused_flags + c->band1->plan.nitems : nullptr;
     }
@@ -516,12 +519,28 @@ static int run_cr_fused(ipxgpu_ctx* c, bool precond, bool zero_start, bool use_r
 
 // Device-resident CR driver. Vectors v_rhs, v_y (initial iterate, only if
 // !zero_start), v_resscale (if use_resscale) must be on the device already.
+// z = inv(S) Ad' inv(E) v for one or two vectors (smw.cuh), on the solve's stream.
+static int launch_smw_pass(ipxgpu_ctx* c, const double* v0, const double* v1, int which,
+                           const CrState* st) {
+    const SmwDev& S = c->smw;
+    smw_gather_kernel<<<S.nchunks, kBlock, 0, c->stream>>>(S, c->diag, v0, v1, which, st);
+    smw_solve_kernel<<<1, kSmwSolveThreads, 0, c->stream>>>(S, which, st);
+    c->launches += 2;
+    IPXGPU_CUDA(cudaGetLastError());
+    return IPXGPU_OK;
+}
+
+static int smw_grid(const ipxgpu_ctx* c) {
+    return c->smw.warp_rows ? grid_for(c, (long long)c->m * 32) : grid_for(c, c->m);
+}
+
 static int run_cr(ipxgpu_ctx* c, int op, bool precond, bool zero_start, bool use_resscale,
                   double tol, int64_t maxiter, ipxgpu_cr_result* result,
                   ipxgpu_interrupt_fn interrupt, void* user, int64_t hist_cap) {
     const int m = (int)c->m;
     if (maxiter < 0) maxiter = c->m + 100;
-    if (op == 0 && fused_available(c))
+    const bool smw = precond && c->smw_active;  // preconditioner with a dense-column part
+    if (op == 0 && fused_available(c) && !smw)
         return run_cr_fused(c, precond, zero_start, use_resscale, tol, maxiter, result, interrupt,
                             user, hist_cap);
     const int grid = grid_for(c, m);
@@ -570,18 +589,35 @@ static int run_cr(ipxgpu_ctx* c, int op, bool precond, bool zero_start, bool use
         cr_init_kernel<<<grid, kBlock, 0, c->stream>>>(v, c->v_rhs, c->v_Cs, c->red, st);
     }
     c->launches++;
+    const int sgrid = smw ? smw_grid(c) : 0;
+    if (smw) {
+        // s = inv(P) r with the dense-column part (cr_init_kernel's s = r ./ E is replaced)
+        IPXGPU_TRY(ensure_reduce(c, std::max(grid, sgrid)));
+        IPXGPU_TRY(launch_smw_pass(c, c->v_r, nullptr, kSmwFirst, nullptr));
+        cr_init_smw_kernel<<<sgrid, kBlock, 0, c->stream>>>(v, c->smw, c->red, st);
+        c->launches++;
+    }
+    // Direction stage: p, Cp, q = P Cp, the dots and the tests; with a dense-column part the
+    // preconditioner apply needs the complete Cp first.
+    auto direction = [&]() -> int {
+        cr_direction_kernel<<<grid, kBlock, 0, c->stream>>>(v, c->red, st, smw ? 1 : 0);
+        c->launches++;
+        if (smw) {
+            IPXGPU_TRY(launch_smw_pass(c, c->v_Cp, c->v_r, kSmwRecompute, st));
+            cr_direction_smw_kernel<<<sgrid, kBlock, 0, c->stream>>>(v, c->smw, c->red, st);
+            c->launches++;
+        }
+        return IPXGPU_OK;
+    };
     IPXGPU_TRY(launch_operator(c, op, precond ? c->v_s : c->v_r, c->v_Cs, kApplyCrInit, st));
-    cr_direction_kernel<<<grid, kBlock, 0, c->stream>>>(v, c->red, st);
-    c->launches++;
+    IPXGPU_TRY(direction());
     IPXGPU_CUDA(cudaGetLastError());
 
     auto enqueue_pass = [&]() -> int {
         cr_update_kernel<<<grid, kBlock, 0, c->stream>>>(v, c->red, st);
         c->launches++;
         IPXGPU_TRY(launch_operator(c, op, precond ? c->v_s : c->v_r, c->v_Cs, kApplyCrIter, st));
-        cr_direction_kernel<<<grid, kBlock, 0, c->stream>>>(v, c->red, st);
-        c->launches++;
-        return IPXGPU_OK;
+        return direction();
     };
 
     const int kBatch = 8;
@@ -747,6 +783,8 @@ int ipxgpu_partition_columns(int64_t n, const int64_t* AIp, int32_t nranks, int6
     return IPXGPU_OK;
 }
 
+static void free_smw(ipxgpu_ctx* c);
+
 void ipxgpu_destroy(ipxgpu_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
@@ -762,6 +800,8 @@ void ipxgpu_destroy(ipxgpu_ctx* c) {
     dev_free(c->tri_err);
     dev_free(c->fused_tickets);
     dev_free(c->fused_flags);
+    free_smw(c);
+    dev_free(c->W_mask);
     dev_free(c->fused_red);
     if (c->band1) { free_band(c->band1); delete c->band1; }
     if (c->band2) { free_band(c->band2); delete c->band2; }
@@ -1287,13 +1327,14 @@ int ipxgpu_normal_apply(ipxgpu_ctx* c, const double* rhs, double* lhs, double* r
 
 // ---- DiagonalPrecond ----
 
-int ipxgpu_diag_factorize(ipxgpu_ctx* c, const double* W, int use_prepared) {
-    IPXGPU_TRY(check_ctx(c));
-    const double *Wc, *Ws;
+// Device pointers of the weights a diagonal build uses: the prepared ones, a staged upload of
+// W, or none (W = 1 on structurals, 0 on slacks).
+static int diag_weights(ipxgpu_ctx* c, const double* W, int use_prepared, const double** Wc,
+                        const double** Ws) {
     if (use_prepared) {
         if (!c->prepared) return fail(IPXGPU_ERR_STATE, "normal matrix not prepared");
-        Wc = c->Wc;
-        Ws = c->Ws;
+        *Wc = c->Wc;
+        *Ws = c->Ws;
     } else if (W) {
         // Stage into the tail of the n-vector scratch so the prepared weights
         // of the normal matrix stay intact.
@@ -1303,17 +1344,166 @@ int ipxgpu_diag_factorize(ipxgpu_ctx* c, const double* W, int use_prepared) {
                                     cudaMemcpyHostToDevice, c->stream));
         IPXGPU_CUDA(cudaMemcpyAsync(stage + c->nloc, W + c->n, sizeof(double) * c->m,
                                     cudaMemcpyHostToDevice, c->stream));
-        Wc = stage;
-        Ws = stage + c->nloc;
+        *Wc = stage;
+        *Ws = stage + c->nloc;
     } else {
-        Wc = nullptr;
-        Ws = nullptr;
+        *Wc = nullptr;
+        *Ws = nullptr;
     }
+    return IPXGPU_OK;
+}
+
+static void free_smw(ipxgpu_ctx* c) {
+    SmwDev& S = c->smw;
+    dev_free(S.colptr); dev_free(S.rowidx); dev_free(S.colval);
+    dev_free(S.rowptr); dev_free(S.colidx); dev_free(S.rowval);
+    dev_free(S.chunk_col); dev_free(S.chunk_p0); dev_free(S.col_chunk0);
+    dev_free(S.partials); dev_free(S.L); dev_free(S.z);
+    S = SmwDev();
+    c->smw_active = false;
+}
+
+int ipxgpu_diag_factorize(ipxgpu_ctx* c, const double* W, int use_prepared) {
+    IPXGPU_TRY(check_ctx(c));
+    const double *Wc, *Ws;
+    IPXGPU_TRY(diag_weights(c, W, use_prepared, &Wc, &Ws));
     if (c->panels.empty())
         IPXGPU_CUDA(cudaMemsetAsync(c->diag, 0, sizeof(double) * std::max<int64_t>(1, c->m),
                                     c->stream));
     IPXGPU_TRY(launch_diag_build(c, Wc, Ws));
     IPXGPU_CUDA(cudaStreamSynchronize(c->stream));
+    c->smw_active = false;
+    return IPXGPU_OK;
+}
+
+__global__ void __launch_bounds__(kBlock)
+zero_entries_kernel(int count, const int* __restrict__ where, double* x) {
+    const int k = blockIdx.x * kBlock + threadIdx.x;
+    if (k < count) x[where[k]] = 0.0;
+}
+
+int ipxgpu_diag_factorize_masked(ipxgpu_ctx* c, const double* W, int use_prepared, int64_t nd,
+                                 const int64_t* dense_cols) {
+    IPXGPU_TRY(check_ctx(c));
+    if (nd < 0 || (nd > 0 && !dense_cols)) return fail(IPXGPU_ERR_ARGUMENT, "dense column list");
+    const double *Wc, *Ws;
+    IPXGPU_TRY(diag_weights(c, W, use_prepared, &Wc, &Ws));
+    // The shard's structural weights with the dense columns' entries zeroed: those columns
+    // never enter the sum (reference src/diagonal_precond.cc:28-36).
+    std::vector<int> local;
+    for (int64_t k = 0; k < nd; k++) {
+        const int64_t j = dense_cols[k];
+        if (j < 0 || j >= c->n) return fail(IPXGPU_ERR_ARGUMENT, "dense column out of range");
+        if (j >= c->col_begin && j < c->col_end) local.push_back((int)(j - c->col_begin));
+    }
+    if (c->nloc > 0) {
+        if (!c->W_mask) IPXGPU_TRY(dev_alloc(&c->W_mask, (size_t)c->nloc));
+        if (Wc)
+            IPXGPU_CUDA(cudaMemcpyAsync(c->W_mask, Wc, sizeof(double) * c->nloc,
+                                        cudaMemcpyDeviceToDevice, c->stream));
+        else
+            fill_kernel<<<grid_for(c, c->nloc), kBlock, 0, c->stream>>>(c->nloc, c->W_mask, 1.0);
+        if (!local.empty()) {
+            int* where = nullptr;
+            IPXGPU_TRY(upload(&where, local, c->stream));
+            zero_entries_kernel<<<((int)local.size() + kBlock - 1) / kBlock, kBlock, 0, c->stream>>>(
+                (int)local.size(), where, c->W_mask);
+            c->launches++;
+            IPXGPU_CUDA(cudaStreamSynchronize(c->stream));
+            dev_free(where);
+        }
+    }
+    if (c->panels.empty())
+        IPXGPU_CUDA(cudaMemsetAsync(c->diag, 0, sizeof(double) * std::max<int64_t>(1, c->m),
+                                    c->stream));
+    IPXGPU_TRY(launch_diag_build(c, c->W_mask, Ws));
+    IPXGPU_CUDA(cudaStreamSynchronize(c->stream));
+    c->smw_active = false;  // until ipxgpu_smw_load installs the factor that belongs to this E
+    return IPXGPU_OK;
+}
+
+int ipxgpu_smw_clear(ipxgpu_ctx* c) {
+    IPXGPU_TRY(check_ctx(c));
+    c->smw_active = false;
+    return IPXGPU_OK;
+}
+
+int ipxgpu_smw_load(ipxgpu_ctx* c, int64_t nd, const int64_t* Adp, const int64_t* Adi,
+                    const double* Adx, const double* L) {
+    IPXGPU_TRY(check_ctx(c));
+    if (nd <= 0 || nd > kSmwMaxCols || !Adp || !L)
+        return fail(IPXGPU_ERR_ARGUMENT, "ipxgpu_smw_load: 1 <= nd <= 1024 dense columns");
+    const int m = (int)c->m;
+    const int64_t nnz = Adp[nd];
+    if (nnz > 0 && (!Adi || !Adx)) return fail(IPXGPU_ERR_ARGUMENT, "ipxgpu_smw_load: null entries");
+    if (nnz >= (int64_t)INT32_MAX) return fail(IPXGPU_ERR_UNSUPPORTED, "dense columns too large");
+    if (!c->diag_ready) return fail(IPXGPU_ERR_STATE, "diagonal not factorized");
+    free_smw(c);
+    SmwDev& S = c->smw;
+    S.nd = (int)nd;
+    S.m = m;
+    // by column, by row (columns ascending inside a row), and the gather chunks
+    std::vector<int> colptr((size_t)nd + 1), rowidx((size_t)nnz), rowptr((size_t)m + 1, 0),
+        colidx((size_t)nnz), chunk_col, chunk_p0, col_chunk0((size_t)nd + 1);
+    std::vector<double> rowval((size_t)nnz);
+    for (int64_t k = 0; k <= nd; k++) colptr[k] = (int)Adp[k];
+    for (int64_t p = 0; p < nnz; p++) {
+        if (Adi[p] < 0 || Adi[p] >= m) return fail(IPXGPU_ERR_ARGUMENT, "dense column: row index");
+        rowidx[p] = (int)Adi[p];
+        rowptr[Adi[p] + 1]++;
+    }
+    for (int i = 0; i < m; i++) rowptr[i + 1] += rowptr[i];
+    {
+        std::vector<int> next(rowptr.begin(), rowptr.end() - 1);
+        for (int64_t k = 0; k < nd; k++)
+            for (int64_t p = Adp[k]; p < Adp[k + 1]; p++) {
+                const int q = next[Adi[p]]++;
+                colidx[q] = (int)k;
+                rowval[q] = Adx[p];
+            }
+    }
+    for (int64_t k = 0; k < nd; k++) {
+        col_chunk0[k] = (int)chunk_col.size();
+        for (int64_t p = Adp[k]; p < Adp[k + 1]; p += kSmwChunk) {
+            chunk_col.push_back((int)k);
+            chunk_p0.push_back((int)p);
+        }
+        if (Adp[k] == Adp[k + 1]) {  // keep one (empty) chunk per column
+            chunk_col.push_back((int)k);
+            chunk_p0.push_back((int)Adp[k]);
+        }
+    }
+    col_chunk0[nd] = (int)chunk_col.size();
+    chunk_p0.push_back((int)nnz);
+    S.nchunks = (int)chunk_col.size();
+    std::vector<int> chunk_end((size_t)S.nchunks);
+    for (int cidx = 0; cidx < S.nchunks; cidx++) {
+        const int k = chunk_col[cidx];
+        chunk_end[cidx] = std::min(colptr[k + 1], chunk_p0[cidx] + kSmwChunk);
+    }
+    // The kernel reads a chunk's range as [chunk_p0[c], chunk_p0[c+1]): columns are contiguous
+    // in Adp and chunks are in entry order, so chunk c+1 begins where chunk c ends.
+    for (int cidx = 0; cidx + 1 < S.nchunks; cidx++)
+        if (chunk_end[cidx] != chunk_p0[cidx + 1])
+            return fail(IPXGPU_ERR_ARGUMENT, "ipxgpu_smw_load: Adp not contiguous");
+    std::vector<double> colval(Adx, Adx + nnz);
+    IPXGPU_TRY(upload(&S.colptr, colptr, c->stream));
+    IPXGPU_TRY(upload(&S.rowidx, rowidx, c->stream));
+    IPXGPU_TRY(upload(&S.colval, colval, c->stream));
+    IPXGPU_TRY(upload(&S.rowptr, rowptr, c->stream));
+    IPXGPU_TRY(upload(&S.colidx, colidx, c->stream));
+    IPXGPU_TRY(upload(&S.rowval, rowval, c->stream));
+    IPXGPU_TRY(upload(&S.chunk_col, chunk_col, c->stream));
+    IPXGPU_TRY(upload(&S.chunk_p0, chunk_p0, c->stream));
+    IPXGPU_TRY(upload(&S.col_chunk0, col_chunk0, c->stream));
+    IPXGPU_TRY(dev_alloc(&S.partials, 2 * (size_t)S.nchunks));
+    IPXGPU_TRY(dev_alloc(&S.z, 2 * (size_t)kSmwMaxCols));
+    IPXGPU_TRY(dev_alloc(&S.L, (size_t)nd * nd));
+    IPXGPU_CUDA(cudaMemcpyAsync(S.L, L, sizeof(double) * nd * nd, cudaMemcpyHostToDevice,
+                                c->stream));
+    S.warp_rows = nnz > 16 * (int64_t)std::max(1, m) ? 1 : 0;
+    IPXGPU_CUDA(cudaStreamSynchronize(c->stream));
+    c->smw_active = true;
     return IPXGPU_OK;
 }
 
@@ -1343,8 +1533,16 @@ int ipxgpu_diag_apply(ipxgpu_ctx* c, const double* rhs, double* lhs, double* rhs
     IPXGPU_TRY(ensure_reduce(c, grid));
     IPXGPU_CUDA(cudaMemcpyAsync(c->xin, rhs, sizeof(double) * m, cudaMemcpyHostToDevice,
                                 c->stream));
-    diag_apply_kernel<<<grid, kBlock, 0, c->stream>>>(m, c->diag, c->xin, c->ybuf, c->red,
-                                                      c->ybuf + m);
+    if (c->smw_active) {
+        const int sgrid = smw_grid(c);
+        IPXGPU_TRY(ensure_reduce(c, sgrid));
+        IPXGPU_TRY(launch_smw_pass(c, c->xin, nullptr, kSmwFirst, nullptr));
+        smw_apply_finish_kernel<<<sgrid, kBlock, 0, c->stream>>>(c->smw, c->diag, c->xin, c->ybuf,
+                                                                 c->red, c->ybuf + m);
+    } else {
+        diag_apply_kernel<<<grid, kBlock, 0, c->stream>>>(m, c->diag, c->xin, c->ybuf, c->red,
+                                                          c->ybuf + m);
+    }
     c->launches++;
     IPXGPU_CUDA(cudaGetLastError());
     IPXGPU_CUDA(cudaMemcpyAsync(lhs, c->ybuf, sizeof(double) * m, cudaMemcpyDeviceToHost,
@@ -1484,6 +1682,7 @@ int ipxgpu_kktdiag_factorize(ipxgpu_ctx* c, const double* xl, const double* xu, 
     IPXGPU_CUDA(cudaGetLastError());
     IPXGPU_TRY(ipxgpu_normal_prepare_dev(c, c->W_full));
     IPXGPU_TRY(launch_diag_build(c, c->Wc, c->Ws));
+    c->smw_active = false;  // a dense-column part belongs to the diagonal it was built for
     if (W_out)
         IPXGPU_CUDA(cudaMemcpyAsync(W_out, c->W_full, sizeof(double) * nm, cudaMemcpyDeviceToHost,
                                     c->stream));

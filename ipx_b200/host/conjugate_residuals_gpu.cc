@@ -2,19 +2,19 @@
 // UNMODIFIED reference header src/conjugate_residuals.h:21-71 and is linked
 // instead of src/conjugate_residuals.cc.
 //
-// When the operators are the device-backed NormalMatrix / DiagonalPrecond /
-// SplittedNormalMatrix (the only LinearOperator implementers in IPX), the whole
-// loop runs device-resident through ipxgpu_pcr_solve / ipxgpu_cr_solve: the
-// scalars never visit the host and Control::InterruptCheck is polled between
-// batches of enqueued iterations. Any other LinearOperator pair (none exists
-// in the reference tree; kept to honour the class contract, e.g. the
-// dense-column preconditioner) is driven through Apply() from the host with
-// the same sequence of tests.
+// The operators are the device-backed NormalMatrix / DiagonalPrecond /
+// SplittedNormalMatrix (the only LinearOperator implementers in IPX): the whole
+// loop runs device-resident through ipxgpu_pcr_solve / ipxgpu_cr_solve, the
+// scalars never visit the host and Control::InterruptCheck is polled while the
+// device iterates. There is no host loop: a LinearOperator without a device twin
+// (none exists in the reference tree) is refused with std::logic_error, which
+// LpSolver::Solve reports as IPX_STATUS_internal_error (src/lp_solver.cc:98-105).
 
 #include "conjugate_residuals.h"
 
 #include <algorithm>
 #include <cmath>
+#include <stdexcept>
 
 #include "gpu_bridge.h"
 #include "timer.h"
@@ -51,13 +51,6 @@ void AddTimes(OperatorRecord* C, OperatorRecord* P, const ipxgpu_cr_result& res)
     if (P && P->time) *P->time += res.time_pre;
 }
 
-double ScaledInfnorm(const Vector& v, const double* resscale) {
-    if (!resscale) return Infnorm(v);
-    double norm = 0.0;
-    for (size_t i = 0; i < v.size(); i++) norm = std::max(norm, std::abs(resscale[i] * v[i]));
-    return norm;
-}
-
 }  // namespace
 
 ConjugateResiduals::ConjugateResiduals(const Control& control) : control_(control) {}
@@ -89,38 +82,8 @@ void ConjugateResiduals::Solve(LinearOperator& C, const Vector& rhs, double tol,
         return;
     }
 
-    // Host-driven loop over Apply() for operators without a device twin.
-    Vector residual(m), step(m), Cresidual(m), Cstep(m);
-    double cdot = 0.0;
-    if (maxiter < 0) maxiter = m + 100;
-    if (Infnorm(lhs) == 0.0) {
-        residual = rhs;
-    } else {
-        C.Apply(lhs, residual, nullptr);
-        residual = rhs - residual;
-    }
-    C.Apply(residual, Cresidual, &cdot);
-    step = residual;
-    Cstep = Cresidual;
-    for (;;) {
-        const double resnorm = ScaledInfnorm(residual, resscale);
-        if (resnorm <= tol) break;
-        if (iter_ == maxiter) { errflag_ = IPX_ERROR_cr_iter_limit; break; }
-        if (cdot <= 0.0) { errflag_ = IPX_ERROR_cr_matrix_not_posdef; break; }
-        const double alpha = cdot / Dot(Cstep, Cstep);
-        if (!std::isfinite(alpha)) { errflag_ = IPX_ERROR_cr_inf_or_nan; break; }
-        lhs += alpha * step;
-        residual -= alpha * Cstep;
-        double cdotnew;
-        C.Apply(residual, Cresidual, &cdotnew);
-        const double beta = cdotnew / cdot;
-        step = residual + beta * step;
-        Cstep = Cresidual + beta * Cstep;
-        cdot = cdotnew;
-        iter_++;
-        if ((errflag_ = control_.InterruptCheck()) != 0) break;
-    }
-    time_ = timer.Elapsed();
+    throw std::logic_error("ConjugateResiduals: operator has no device twin (expected NormalMatrix "
+                           "or SplittedNormalMatrix, prepared on the current device context)");
 }
 
 // Reference src/conjugate_residuals.cc:90-213.
@@ -135,7 +98,7 @@ void ConjugateResiduals::Solve(LinearOperator& C, LinearOperator& P, const Vecto
     OperatorRecord* devC = DeviceOperator(C);
     OperatorRecord* devP = ipxb200::FindRecord(&P);
     const bool device_loop = devC && devC->kind == OperatorKind::kNormal && devP &&
-                             devP->kind == OperatorKind::kDiagonal && !devP->host_part &&
+                             devP->kind == OperatorKind::kDiagonal &&
                              ipxb200::StillCurrent(*devP) && devP->ref.ctx == devC->ref.ctx;
     if (device_loop) {
         ipxgpu_cr_result res{};
@@ -158,49 +121,9 @@ void ConjugateResiduals::Solve(LinearOperator& C, LinearOperator& P, const Vecto
         return;
     }
 
-    // Host-driven loop (e.g. preconditioner with a dense-column part).
-    Vector residual(m), sresidual(m), step(m), Csresidual(m), Cstep(m), PCstep(m);
-    double cdot = 0.0, rho = 0.0;
-    if (maxiter < 0) maxiter = m + 100;
-    if (Infnorm(lhs) == 0.0) {
-        residual = rhs;
-    } else {
-        C.Apply(lhs, residual, nullptr);
-        residual = rhs - residual;
-    }
-    P.Apply(residual, sresidual, &rho);
-    C.Apply(sresidual, Csresidual, &cdot);
-    step = sresidual;
-    Cstep = Csresidual;
-    for (;;) {
-        const double resnorm = ScaledInfnorm(residual, resscale);
-        if (resnorm <= tol) break;
-        if (iter_ == maxiter) { errflag_ = IPX_ERROR_cr_iter_limit; break; }
-        if (cdot <= 0.0) { errflag_ = IPX_ERROR_cr_matrix_not_posdef; break; }
-        double pdot;
-        P.Apply(Cstep, PCstep, &pdot);
-        if (pdot <= 0.0) { errflag_ = IPX_ERROR_cr_precond_not_posdef; break; }
-        const double alpha = cdot / pdot;
-        if (!std::isfinite(alpha)) { errflag_ = IPX_ERROR_cr_inf_or_nan; break; }
-        lhs += alpha * step;
-        residual -= alpha * Cstep;
-        sresidual -= alpha * PCstep;
-        double cdotnew;
-        C.Apply(sresidual, Csresidual, &cdotnew);
-        const double beta = cdotnew / cdot;
-        step = sresidual + beta * step;
-        Cstep = Csresidual + beta * Cstep;
-        cdot = cdotnew;
-        iter_++;
-        if (iter_ % 5 == 0) {
-            double rho_new;
-            P.Apply(residual, sresidual, &rho_new);
-            if (rho_new >= rho) { errflag_ = IPX_ERROR_cr_no_progress; break; }
-            rho = rho_new;
-        }
-        if ((errflag_ = control_.InterruptCheck()) != 0) break;
-    }
-    time_ = timer.Elapsed();
+    throw std::logic_error("ConjugateResiduals: operators have no device twins (expected "
+                           "NormalMatrix and DiagonalPrecond of one model, prepared on the "
+                           "current device context)");
 }
 
 Int ConjugateResiduals::errflag() const { return errflag_; }

@@ -42,7 +42,6 @@ struct OperatorRecord {
     OperatorKind kind = OperatorKind::kNone;
     ContextRef ref;
     const ipx::Model* model = nullptr;
-    bool host_part = false;     // DiagonalPrecond with a dense-column SMW part
     double* time = nullptr;     // NormalMatrix::time_ / DiagonalPrecond::time_
     double* time_B = nullptr;   // SplittedNormalMatrix accumulators
     double* time_Bt = nullptr;

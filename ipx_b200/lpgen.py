@@ -89,6 +89,34 @@ def random_sparse_lp(m, n, k, seed, name=""):
               float(obj @ x0), name or f"random_{m}x{n}_k{k}")
 
 
+def dense_column_lp(m, n, k, ndense, seed, dense_frac=0.5, name=""):
+    """random_sparse_lp plus `ndense` dense columns (a fraction `dense_frac` of the rows each),
+    spread over the column range. Model::FindDenseColumns (reference src/model.cc:34-56) marks
+    a column dense when its count exceeds max(40, 10 x the next smaller count), so these
+    columns take the Sherman-Morrison-Woodbury branch of the diagonal preconditioner
+    (src/diagonal_precond.cc:48-102) under the default precond_dense_cols = 1."""
+    rng = np.random.default_rng(seed)
+    kd = max(41, 10 * k + 1, int(m * dense_frac))
+    assert kd <= m
+    where = np.sort(rng.choice(n, ndense, replace=False))
+    is_dense = np.zeros(n, bool)
+    is_dense[where] = True
+    counts = np.where(is_dense, kd, k).astype(np.int64)
+    Ap = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+    Ai = np.empty(int(Ap[-1]), np.int64)
+    sparse_rows = _distinct_rows(rng, n - ndense, k, np.zeros(n - ndense, np.int64),
+                                 np.full(n - ndense, m, np.int64))
+    starts = Ap[:-1][~is_dense]
+    Ai[(starts[:, None] + np.arange(k)[None, :]).reshape(-1)] = sparse_rows.reshape(-1)
+    for j in where:
+        Ai[Ap[j]:Ap[j + 1]] = np.sort(rng.choice(m, kd, replace=False))
+    Ax = _values(rng, int(Ap[-1]))
+    x0, rhs, obj = _feasible_rhs_obj(rng, m, n, Ap, Ai, Ax)
+    return LP(m, n, Ap, Ai, Ax, rhs, b"=" * m, obj, np.zeros(n), np.full(n, np.inf),
+              float(obj @ x0), name or f"densecols_{m}x{n}_k{k}_d{ndense}",
+              {"dense_cols": [int(j) for j in where], "dense_count": int(kd)})
+
+
 def block_angular_lp(m, n, k, seed, block_rows=200, link_frac=0.005, name=""):
     """Config 3 shape: diagonal blocks of `block_rows` rows plus linking rows.
 

@@ -1,0 +1,58 @@
+"""How far do one-ulp perturbations of the LP data move the REFERENCE's own IPM run? Runs the
+reference build (oracle/_ref) on an LP and on copies whose right-hand side and objective are
+multiplied entrywise by (1 +- 2^-52), and prints the per-iteration CR counts side by side.
+The drop-in build differs from the reference by summation order only, i.e. by perturbations of
+this size inside every operator apply; this tool measures what such perturbations do to the
+iteration path of the unmodified CPU code.
+
+    python tools/ipm_sensitivity.py random:50000:500000:10 --copies 4 [--gpu]
+"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ipx_b200 import e2e, ipxlib, lpgen  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("lp")
+ap.add_argument("--copies", type=int, default=4)
+ap.add_argument("--gpu", action="store_true", help="also run the drop-in build on the unperturbed LP")
+ap.add_argument("--out", default=None)
+args = ap.parse_args()
+kind, *dims = args.lp.split(":")
+d = [int(v) for v in dims]
+lp = (lpgen.random_sparse_lp(d[0], d[1], d[2], 1002) if kind == "random"
+      else lpgen.transportation_lp(d[0], d[1], 1004))
+params = dict(dualize=0, crossover=0, stop_at_switch=-1)
+ref = ipxlib.IpxLibrary(ipxlib.REF_LIB)
+runs = {}
+runs["ref"] = e2e.solve(ref, lp, per_iter=True, **params)
+rng = np.random.default_rng(5)
+for c in range(args.copies):
+    q = lpgen.LP(**{**lp.__dict__})
+    ulp = 2.0 ** -52
+    q.rhs = lp.rhs * (1.0 + ulp * rng.choice(np.array([-1.0, 0.0, 1.0]), lp.m))
+    q.obj = lp.obj * (1.0 + ulp * rng.choice(np.array([-1.0, 0.0, 1.0]), lp.n))
+    runs[f"ref+ulp{c}"] = e2e.solve(ref, q, per_iter=True, **params)
+if args.gpu:
+    runs["gpu"] = e2e.solve(ipxlib.IpxLibrary(ipxlib.GPU_LIB), lp, per_iter=True, **params)
+names = list(runs)
+print("LP", lp.name)
+print("%-10s" % "", " ".join("%10s" % n for n in names))
+print("%-10s" % "IPM iter", " ".join("%10d" % runs[n]["iter"] for n in names))
+print("%-10s" % "CR iter", " ".join("%10d" % runs[n]["kktiter1"] for n in names))
+print("%-10s" % "pobjval", " ".join("%10.6g" % runs[n]["pobjval"] for n in names))
+depth = max(len(runs[n]["per_iter"]) for n in names)
+for k in range(depth):
+    cells = []
+    for n in names:
+        t = runs[n]["per_iter"]
+        cells.append("%4d %5.0e" % (t[k]["kktiter"], t[k]["mu"]) if k < len(t) else "         -")
+    print("%-10s" % f"it {k}", " ".join("%10s" % c for c in cells))
+if args.out:
+    with open(args.out, "w") as f:
+        json.dump({"lp": lp.name, "runs": runs}, f, indent=1)
