@@ -115,6 +115,20 @@ int ipxgpu_comm_init(ipxgpu_ctx* ctx, const char id[128]);
 int ipxgpu_peer_export(ipxgpu_ctx* ctx, char handle[64]);
 int ipxgpu_peer_import(ipxgpu_ctx* ctx, const char* handles);
 
+/* One process, several GPUs: creates ngpus column-sharded contexts (nnz-balanced, one per
+ * device; devices == NULL: ordinals 0..ngpus-1), their NCCL communicator and their NVLink peer
+ * exchange (cudaDeviceEnablePeerAccess), and returns ONE handle. Calls on the handle block and
+ * run the ranks on one host thread each. The handle accepts the entry points KKTSolverDiag
+ * needs - ipxgpu_kktdiag_factorize, ipxgpu_kktdiag_solve (and ipxgpu_get_layout / _tiling of
+ * rank 0, ipxgpu_launch_count, ipxgpu_destroy) - so that an LpSolver user gets the
+ * column-sharded A*D^2*A' of SURVEY.md section 8e without managing processes: the drop-in
+ * build creates such a group when IPXGPU_NGPUS > 1 (ipx_b200/host/gpu_bridge.cc). Other entry
+ * points return IPXGPU_ERR_UNSUPPORTED on a group handle. the rank, column range and stream
+ * fields of opt are ignored. The interrupt callback of a solve is polled by rank 0, all ranks follow it. */
+int ipxgpu_create_group(ipxgpu_ctx** ctx, int64_t m, int64_t n, const int64_t* AIp,
+                        const int64_t* AIi, const double* AIx, const ipxgpu_options* opt,
+                        int32_t ngpus, const int32_t* devices);
+
 /* ---- NormalMatrix (reference src/normal_matrix.h) ---- */
 
 /* NormalMatrix::Prepare (src/normal_matrix.cc:32-35). W: host, n+m entries, or

@@ -38,7 +38,7 @@ EXPORTS = ("ipxgpu_default_options ipxgpu_last_error ipxgpu_device_count ipxgpu_
            "ipxgpu_destroy ipxgpu_get_layout ipxgpu_get_tiling ipxgpu_synchronize ipxgpu_partition_columns ipxgpu_comm_unique_id "
            "ipxgpu_comm_init ipxgpu_normal_prepare ipxgpu_normal_prepare_dev ipxgpu_normal_apply "
            "ipxgpu_normal_apply_dev ipxgpu_diag_factorize ipxgpu_diag_get ipxgpu_diag_set "
-           "ipxgpu_diag_factorize_masked ipxgpu_smw_load ipxgpu_smw_clear "
+           "ipxgpu_diag_factorize_masked ipxgpu_smw_load ipxgpu_smw_clear ipxgpu_create_group "
            "ipxgpu_diag_apply ipxgpu_pcr_solve ipxgpu_pcr_solve_dev ipxgpu_cr_solve ipxgpu_kktdiag_factorize "
            "ipxgpu_kktdiag_solve ipxgpu_lu_load ipxgpu_tri_solve ipxgpu_split_prepare "
            "ipxgpu_split_apply ipxgpu_kktbasis_prepare ipxgpu_basis_solve ipxgpu_kktbasis_solve ipxgpu_time_normal_apply ipxgpu_launch_count ipxgpu_band_selftest ipxgpu_peer_export ipxgpu_peer_import").split()

@@ -111,7 +111,10 @@ struct BandDev;        // band_sweep.cuh
 
 }  // namespace ipxgpu
 
+struct ipxgpu_group;  // ipxgpu.cu: the contexts of a one-process, several-GPU group
+
 struct ipxgpu_ctx {
+    ipxgpu_group* group = nullptr;  // set in a group's handle (which holds no device data)
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
@@ -181,6 +184,7 @@ struct ipxgpu_ctx {
     void* peer_base[16] = {nullptr};  // every rank's exchange buffer as mapped here (own: xchg)
     double** peer_dev = nullptr;      // device copy of peer_base
     bool peers_ready = false;
+    bool peers_direct = false;        // peer_base holds other devices' pointers of THIS process
     unsigned xchg_gen = 0;            // cross-GPU synchronisations performed so far
 
     // persistent CR kernel (pcr_fused.cuh): grid barrier words and per-CTA partials

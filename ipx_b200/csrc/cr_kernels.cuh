@@ -320,4 +320,12 @@ mul_sub_kernel(long long n, const double* __restrict__ a, const double* __restri
         out[j] = __dmul_rn(a[j], b[j]) - c[j];
 }
 
+// x = a - x
+__global__ void __launch_bounds__(kBlock)
+sub_from_kernel(long long n, const double* __restrict__ a, double* x) {
+    for (long long j = (long long)blockIdx.x * kBlock + threadIdx.x; j < n;
+         j += (long long)gridDim.x * kBlock)
+        x[j] = a[j] - x[j];
+}
+
 }  // namespace ipxgpu

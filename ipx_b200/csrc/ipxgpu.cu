@@ -4,6 +4,7 @@
 #include <nccl.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdlib>
@@ -679,6 +680,10 @@ static int run_cr(ipxgpu_ctx* c, int op, bool precond, bool zero_start, bool use
 
 static int check_ctx(const ipxgpu_ctx* c) {
     if (!c) return fail(IPXGPU_ERR_ARGUMENT, "null context");
+    if (c->group)
+        return fail(IPXGPU_ERR_UNSUPPORTED,
+                    "a multi-GPU group drives the KKTSolverDiag entry points only "
+                    "(ipxgpu_kktdiag_factorize / ipxgpu_kktdiag_solve)");
     cudaError_t e = cudaSetDevice(c->device);
     if (e != cudaSuccess) return fail(IPXGPU_ERR_CUDA, cudaGetErrorString(e));
     return IPXGPU_OK;
@@ -687,6 +692,11 @@ static int check_ctx(const ipxgpu_ctx* c) {
 }  // namespace ipxgpu
 
 using namespace ipxgpu;
+
+// The contexts of a one-process, several-GPU group (see ipxgpu_create_group).
+struct ipxgpu_group {
+    std::vector<ipxgpu_ctx*> sub;
+};
 
 // =================================================================== C ABI
 
@@ -785,13 +795,26 @@ int ipxgpu_partition_columns(int64_t n, const int64_t* AIp, int32_t nranks, int6
 
 static void free_smw(ipxgpu_ctx* c);
 
+static void destroy_group(ipxgpu_ctx* c);
+static int group_kktdiag_factorize(ipxgpu_ctx* c, const double* xl, const double* xu,
+                                   const double* zl, const double* zu, double mu, double* W_out,
+                                   double* resscale_out);
+static int group_kktdiag_solve(ipxgpu_ctx* c, const double* a, const double* b, double tol,
+                               int64_t maxiter, double* x, double* y, ipxgpu_cr_result* result,
+                               ipxgpu_interrupt_fn interrupt, void* user);
+
 void ipxgpu_destroy(ipxgpu_ctx* c) {
     if (!c) return;
+    if (c->group) {
+        destroy_group(c);
+        return;
+    }
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     destroy_split(c);
     for (int r = 0; r < c->nranks && r < 16; r++)
-        if (r != c->rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
+        if (r != c->rank && c->peer_base[r] && !c->peers_direct)
+            cudaIpcCloseMemHandle(c->peer_base[r]);
     if (c->xchg) cudaFree(c->xchg);
     dev_free(c->peer_dev);
     dev_free(c->fused_bar);
@@ -1157,6 +1180,7 @@ int ipxgpu_create(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp, co
 
 int ipxgpu_get_layout(ipxgpu_ctx* c, int64_t out[8]) {
     if (!c || !out) return fail(IPXGPU_ERR_ARGUMENT, "null argument");
+    if (c->group) return ipxgpu_get_layout(c->group->sub[0], out);
     int64_t ct = 0, rt = 0;
     for (const Panel& P : c->panels) {
         ct += P.col_tiles.ntiles;
@@ -1168,6 +1192,7 @@ int ipxgpu_get_layout(ipxgpu_ctx* c, int64_t out[8]) {
 }
 
 int ipxgpu_get_tiling(ipxgpu_ctx* c, int64_t out[16]) {
+    if (c && c->group) return ipxgpu_get_tiling(c->group->sub[0], out);
     if (!c || !out) return fail(IPXGPU_ERR_ARGUMENT, "null argument");
     const BandDev* ts[2] = {c->band1, c->band2};
     for (int k = 0; k < 2; k++) {
@@ -1191,6 +1216,11 @@ int ipxgpu_synchronize(ipxgpu_ctx* c) {
 
 int ipxgpu_launch_count(ipxgpu_ctx* c, int64_t* count) {
     if (!c || !count) return fail(IPXGPU_ERR_ARGUMENT, "null argument");
+    if (c->group) {
+        *count = 0;
+        for (ipxgpu_ctx* s : c->group->sub) *count += s->launches;
+        return IPXGPU_OK;
+    }
     *count = c->launches;
     return IPXGPU_OK;
 }
@@ -1208,27 +1238,32 @@ int ipxgpu_comm_unique_id(char id[128]) {
     return IPXGPU_OK;
 }
 
+// Exchange buffer of a sharded context (plain cudaMalloc: IPC-exportable and peer-mappable).
+static int ensure_xchg(ipxgpu_ctx* c) {
+    if (c->nranks < 2 || c->nranks > 16) return fail(IPXGPU_ERR_STATE, "peer exchange needs 2..16 ranks");
+    if (c->xchg) return IPXGPU_OK;
+    c->xchg_mpad = ((size_t)c->m + 31) & ~(size_t)31;
+    // [pull exchange: y[2][mpad] doubles, flags[nranks][SMs]] [push exchange:
+    // records[2][nranks][mpad] of 16 bytes]
+    size_t bytes = 2 * c->xchg_mpad * sizeof(double) +
+                   (size_t)c->nranks * c->num_sms * sizeof(unsigned);
+    bytes = (bytes + 255) & ~(size_t)255;
+    c->xchg_ll_off = bytes;
+    bytes += 2 * (size_t)c->nranks * c->xchg_mpad * 16;  // partial-product records
+    bytes += 2 * c->xchg_mpad * 16;                       // final records (two-phase exchange)
+    IPXGPU_CUDA(cudaMalloc(&c->xchg, bytes));
+    IPXGPU_CUDA(cudaMemset(c->xchg, 0, bytes));
+    c->xchg_gen = 0;
+    IPXGPU_TRY(dev_alloc(&c->xchg_abort, 1));
+    IPXGPU_CUDA(cudaMemset(c->xchg_abort, 0, sizeof(double)));
+    return IPXGPU_OK;
+}
+
 int ipxgpu_peer_export(ipxgpu_ctx* c, char handle[64]) {
     IPXGPU_TRY(check_ctx(c));
     if (!handle) return fail(IPXGPU_ERR_ARGUMENT, "null argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t size");
-    if (c->nranks < 2 || c->nranks > 16) return fail(IPXGPU_ERR_STATE, "peer exchange needs 2..16 ranks");
-    if (!c->xchg) {
-        c->xchg_mpad = ((size_t)c->m + 31) & ~(size_t)31;
-        // [pull exchange: y[2][mpad] doubles, flags[nranks][SMs]] [push exchange:
-        // records[2][nranks][mpad] of 16 bytes]
-        size_t bytes = 2 * c->xchg_mpad * sizeof(double) +
-                       (size_t)c->nranks * c->num_sms * sizeof(unsigned);
-        bytes = (bytes + 255) & ~(size_t)255;
-        c->xchg_ll_off = bytes;
-        bytes += 2 * (size_t)c->nranks * c->xchg_mpad * 16;  // partial-product records
-        bytes += 2 * c->xchg_mpad * 16;                       // final records (two-phase exchange)
-        IPXGPU_CUDA(cudaMalloc(&c->xchg, bytes));  // plain cudaMalloc: IPC-exportable
-        IPXGPU_CUDA(cudaMemset(c->xchg, 0, bytes));
-        c->xchg_gen = 0;
-        IPXGPU_TRY(dev_alloc(&c->xchg_abort, 1));
-        IPXGPU_CUDA(cudaMemset(c->xchg_abort, 0, sizeof(double)));
-    }
+    IPXGPU_TRY(ensure_xchg(c));
     cudaIpcMemHandle_t h;
     IPXGPU_CUDA(cudaIpcGetMemHandle(&h, c->xchg));
     std::memcpy(handle, &h, 64);
@@ -1641,15 +1676,44 @@ int ipxgpu_cr_solve(ipxgpu_ctx* c, int op, const double* rhs, double tol, const 
 
 // ---- KKTSolverDiag ----
 
+// Largest of a scalar over the ranks (NCCL max; nranks == 1: nothing to do).
+static int allreduce_max(ipxgpu_ctx* c, double* buf, size_t count) {
+    if (c->nranks == 1) return IPXGPU_OK;
+    if (!c->nccl_comm)
+        return fail(IPXGPU_ERR_STATE, "nranks > 1 but ipxgpu_comm_init was not called");
+    NcclApi* api = nccl_api();
+    ncclResult_t r = api->AllReduce(buf, buf, count, ncclDouble, ncclMax,
+                                    (ncclComm_t)c->nccl_comm, c->stream);
+    if (r != ncclSuccess)
+        return fail(IPXGPU_ERR_NCCL, std::string("ncclAllReduce(max): ") +
+                                         (api->GetErrorString ? api->GetErrorString(r) : "?"));
+    return IPXGPU_OK;
+}
+
+// The KKTSolverDiag entry points work in the shard's LOCAL layout [nloc structural columns of
+// the shard | m slack columns]: with one rank that is the whole (n+m)-vector; with column
+// shards every rank holds its columns' part of the iterate, of W, of a and of x plus a replica
+// of the slack part, and the three m-vectors that sum over columns (diagonal, right-hand side,
+// slack part of x) are allreduced.
+static int upload_local(ipxgpu_ctx* c, double* dst, const double* src_full) {
+    if (c->nloc > 0)
+        IPXGPU_CUDA(cudaMemcpyAsync(dst, src_full + c->col_begin, sizeof(double) * c->nloc,
+                                    cudaMemcpyHostToDevice, c->stream));
+    if (c->m > 0)
+        IPXGPU_CUDA(cudaMemcpyAsync(dst + c->nloc, src_full + c->n, sizeof(double) * c->m,
+                                    cudaMemcpyHostToDevice, c->stream));
+    return IPXGPU_OK;
+}
+
 int ipxgpu_kktdiag_factorize(ipxgpu_ctx* c, const double* xl, const double* xu, const double* zl,
                              const double* zu, double mu, double* W_out, double* resscale_out) {
+    if (c && c->group)
+        return group_kktdiag_factorize(c, xl, xu, zl, zu, mu, W_out, resscale_out);
     IPXGPU_TRY(check_ctx(c));
-    if (c->nranks != 1)
-        return fail(IPXGPU_ERR_UNSUPPORTED, "kktdiag entry points need an unsharded context");
-    const long long nm = c->n + c->m;
-    if (!c->W_full) IPXGPU_TRY(dev_alloc(&c->W_full, (size_t)nm));
+    const long long nl = (long long)c->nloc + c->m;  // local layout
+    if (!c->W_full) IPXGPU_TRY(dev_alloc(&c->W_full, (size_t)(c->n + c->m)));
     if (!c->resscale_kkt) IPXGPU_TRY(dev_alloc(&c->resscale_kkt, (size_t)c->m));
-    const int grid = grid_for(c, nm);
+    const int grid = grid_for(c, nl);
     IPXGPU_TRY(ensure_reduce(c, grid));
     c->kkt_factorized = false;
     if (xl) {
@@ -1662,31 +1726,39 @@ int ipxgpu_kktdiag_factorize(ipxgpu_ctx* c, const double* xl, const double* xu, 
         double* d_zl = c->nvec[2];
         double* d_zu = c->nvec[3];
         cudaStream_t s = c->stream;
-        auto up = [&](double* d, const double* h) {
-            return cudaMemcpyAsync(d, h, sizeof(double) * nm, cudaMemcpyHostToDevice, s);
-        };
-        cudaError_t e1 = up(d_xl, xl), e2 = up(d_xu, xu), e3 = up(d_zl, zl), e4 = up(d_zu, zu);
-        if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess)
-            return fail(IPXGPU_ERR_CUDA, "iterate upload failed");
-        kkt_weights_kernel<<<grid, kBlock, 0, s>>>(nm, d_xl, d_xu, d_zl, d_zu, c->W_full, c->red,
+        IPXGPU_TRY(upload_local(c, d_xl, xl));
+        IPXGPU_TRY(upload_local(c, d_xu, xu));
+        IPXGPU_TRY(upload_local(c, d_zl, zl));
+        IPXGPU_TRY(upload_local(c, d_zu, zu));
+        kkt_weights_kernel<<<grid, kBlock, 0, s>>>(nl, d_xl, d_xu, d_zl, d_zu, c->W_full, c->red,
                                                    c->scalars);
-        kkt_weights_fix_kernel<<<grid, kBlock, 0, s>>>(nm, c->n, c->W_full, c->resscale_kkt, mu,
+        // regval is the smallest nonzero g over ALL columns (reference :34-41)
+        IPXGPU_TRY(allreduce_max(c, c->scalars, 1));
+        kkt_weights_fix_kernel<<<grid, kBlock, 0, s>>>(nl, c->nloc, c->W_full, c->resscale_kkt, mu,
                                                        c->scalars);
         c->launches += 2;
         IPXGPU_CUDA(cudaStreamSynchronize(s));
     } else {
-        fill_kernel<<<grid, kBlock, 0, c->stream>>>(nm, c->W_full, 1.0);
+        fill_kernel<<<grid, kBlock, 0, c->stream>>>(nl, c->W_full, 1.0);
         fill_kernel<<<grid_for(c, c->m), kBlock, 0, c->stream>>>(c->m, c->resscale_kkt, 1.0);
         c->launches += 2;
     }
     IPXGPU_CUDA(cudaGetLastError());
-    IPXGPU_TRY(ipxgpu_normal_prepare_dev(c, c->W_full));
+    c->Wc = c->W_full;
+    c->Ws = c->W_full + c->nloc;
+    c->prepared = true;
     IPXGPU_TRY(launch_diag_build(c, c->Wc, c->Ws));
     c->smw_active = false;  // a dense-column part belongs to the diagonal it was built for
-    if (W_out)
-        IPXGPU_CUDA(cudaMemcpyAsync(W_out, c->W_full, sizeof(double) * nm, cudaMemcpyDeviceToHost,
-                                    c->stream));
-    if (resscale_out)
+    if (W_out) {
+        // this rank's columns; the slack part once (identical on every rank)
+        if (c->nloc > 0)
+            IPXGPU_CUDA(cudaMemcpyAsync(W_out + c->col_begin, c->W_full, sizeof(double) * c->nloc,
+                                        cudaMemcpyDeviceToHost, c->stream));
+        if (c->rank == 0 && c->m > 0)
+            IPXGPU_CUDA(cudaMemcpyAsync(W_out + c->n, c->W_full + c->nloc, sizeof(double) * c->m,
+                                        cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (resscale_out && c->rank == 0)
         IPXGPU_CUDA(cudaMemcpyAsync(resscale_out, c->resscale_kkt, sizeof(double) * c->m,
                                     cudaMemcpyDeviceToHost, c->stream));
     IPXGPU_CUDA(cudaStreamSynchronize(c->stream));
@@ -1697,22 +1769,30 @@ int ipxgpu_kktdiag_factorize(ipxgpu_ctx* c, const double* xl, const double* xu, 
 int ipxgpu_kktdiag_solve(ipxgpu_ctx* c, const double* a, const double* b, double tol,
                          int64_t maxiter, double* x, double* y, ipxgpu_cr_result* result,
                          ipxgpu_interrupt_fn interrupt, void* user) {
+    if (c && c->group)
+        return group_kktdiag_solve(c, a, b, tol, maxiter, x, y, result, interrupt, user);
     IPXGPU_TRY(check_ctx(c));
     if (!c->kkt_factorized) return fail(IPXGPU_ERR_STATE, "kktdiag not factorized");
     if (!a || !b || !x || !y) return fail(IPXGPU_ERR_ARGUMENT, "null vector");
     const auto t0 = std::chrono::steady_clock::now();
-    const long long n = c->n, m = c->m, nm = n + m;
+    const long long nloc = c->nloc, m = c->m;
+    const bool lead = c->rank == 0;
     IPXGPU_TRY(ensure_nvecs(c));
     IPXGPU_TRY(ensure_cr_buffers(c, 0));
     cudaStream_t s = c->stream;
     double* d_a = c->nvec[0];
     double* d_u = c->nvec[1];  // W.*a, later x
     double* d_b = c->xin;
-    IPXGPU_CUDA(cudaMemcpyAsync(d_a, a, sizeof(double) * nm, cudaMemcpyHostToDevice, s));
+    IPXGPU_TRY(upload_local(c, d_a, a));
     IPXGPU_CUDA(cudaMemcpyAsync(d_b, b, sizeof(double) * m, cudaMemcpyHostToDevice, s));
-    // rhs = -b + AI*(W.*a)  (reference src/kkt_solver_diag.cc:90-92)
-    mul_kernel<<<grid_for(c, n), kBlock, 0, s>>>(n, c->W_full, d_a, d_u);
-    mul_sub_kernel<<<grid_for(c, m), kBlock, 0, s>>>(m, c->W_full + n, d_a + n, d_b, c->ybuf);
+    // rhs = -b + AI*(W.*a)  (reference src/kkt_solver_diag.cc:90-92); the slack columns' term
+    // and -b enter once (rank 0), the structural columns' terms are summed over the ranks
+    mul_kernel<<<grid_for(c, nloc), kBlock, 0, s>>>(nloc, c->W_full, d_a, d_u);
+    if (lead)
+        mul_sub_kernel<<<grid_for(c, m), kBlock, 0, s>>>(m, c->W_full + nloc, d_a + nloc, d_b,
+                                                         c->ybuf);
+    else
+        IPXGPU_CUDA(cudaMemsetAsync(c->ybuf, 0, sizeof(double) * m, s));
     c->launches += 2;
     if (c->panels.empty())
         IPXGPU_CUDA(cudaMemcpyAsync(c->v_rhs, c->ybuf, sizeof(double) * m,
@@ -1722,30 +1802,224 @@ int ipxgpu_kktdiag_solve(ipxgpu_ctx* c, const double* a, const double* b, double
         OpRowAffine op{d_u, c->ybuf, c->v_rhs, 1.0, k == 0};
         IPXGPU_TRY(launch_sweep(c, op, P.row_tiles, P.csr, nullptr));
     }
+    IPXGPU_TRY(allreduce_sum(c, c->v_rhs, (size_t)m));
     // y = 0; PCR with resscale (reference :95-99)
     IPXGPU_CUDA(cudaMemcpyAsync(c->v_resscale, c->resscale_kkt, sizeof(double) * m,
                                 cudaMemcpyDeviceToDevice, s));
     IPXGPU_TRY(run_cr(c, 0, true, true, true, tol, maxiter, result, interrupt, user, 0));
     // Recovery (reference :108-117): x[j] = W[j]*(a[j] - A[:,j]'y);
-    // x[n+i] = b[i] - sum_j x[j] a_ij.
+    // x[n+i] = b[i] - sum_j x[j] a_ij (the sum over all ranks' columns).
     for (size_t k = 0; k < c->panels.size(); k++) {
         const Panel& P = c->panels[k];
         OpColRecover op{c->v_y, c->W_full, d_a, d_u};
         IPXGPU_TRY(launch_sweep(c, op, P.col_tiles, c->csc, nullptr));
     }
-    if (c->panels.empty())
-        IPXGPU_CUDA(cudaMemcpyAsync(d_u + n, d_b, sizeof(double) * m, cudaMemcpyDeviceToDevice, s));
-    for (size_t k = 0; k < c->panels.size(); k++) {
-        const Panel& P = c->panels[k];
-        OpRowAffine op{d_u, d_b, d_u + n, -1.0, k == 0};
-        IPXGPU_TRY(launch_sweep(c, op, P.row_tiles, P.csr, nullptr));
+    double* d_xs = d_u + nloc;  // slack part of x
+    if (c->nranks == 1) {
+        if (c->panels.empty())
+            IPXGPU_CUDA(cudaMemcpyAsync(d_xs, d_b, sizeof(double) * m, cudaMemcpyDeviceToDevice, s));
+        for (size_t k = 0; k < c->panels.size(); k++) {
+            const Panel& P = c->panels[k];
+            OpRowAffine op{d_u, d_b, d_xs, -1.0, k == 0};
+            IPXGPU_TRY(launch_sweep(c, op, P.row_tiles, P.csr, nullptr));
+        }
+    } else {
+        // partial sums A_g x_g (from zero), summed over the ranks, then b - sum
+        IPXGPU_CUDA(cudaMemsetAsync(c->ybuf, 0, sizeof(double) * m, s));
+        if (c->panels.empty())
+            IPXGPU_CUDA(cudaMemsetAsync(d_xs, 0, sizeof(double) * m, s));
+        for (size_t k = 0; k < c->panels.size(); k++) {
+            const Panel& P = c->panels[k];
+            OpRowAffine op{d_u, c->ybuf, d_xs, 1.0, k == 0};
+            IPXGPU_TRY(launch_sweep(c, op, P.row_tiles, P.csr, nullptr));
+        }
+        IPXGPU_TRY(allreduce_sum(c, d_xs, (size_t)m));
+        sub_from_kernel<<<grid_for(c, m), kBlock, 0, s>>>(m, d_b, d_xs);
+        c->launches++;
     }
-    IPXGPU_CUDA(cudaMemcpyAsync(x, d_u, sizeof(double) * nm, cudaMemcpyDeviceToHost, s));
-    IPXGPU_CUDA(cudaMemcpyAsync(y, c->v_y, sizeof(double) * m, cudaMemcpyDeviceToHost, s));
+    if (nloc > 0)
+        IPXGPU_CUDA(cudaMemcpyAsync(x + c->col_begin, d_u, sizeof(double) * nloc,
+                                    cudaMemcpyDeviceToHost, s));
+    if (lead) {
+        IPXGPU_CUDA(cudaMemcpyAsync(x + c->n, d_xs, sizeof(double) * m, cudaMemcpyDeviceToHost, s));
+        IPXGPU_CUDA(cudaMemcpyAsync(y, c->v_y, sizeof(double) * m, cudaMemcpyDeviceToHost, s));
+    }
     IPXGPU_CUDA(cudaStreamSynchronize(s));
     if (result)
         result->time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return IPXGPU_OK;
+}
+
+
+}  // extern "C"
+
+// ---- one process, several GPUs (IPXGPU_NGPUS of the drop-in build) ----
+//
+// A group is G ordinary sharded contexts, one per device, each driven from its own host thread
+// for the duration of a call (the calls block: the persistent CR kernels of the ranks meet once
+// per iteration over NVLink). NCCL communicator per rank (ncclCommInitRank from G threads),
+// exchange buffers mapped with cudaDeviceEnablePeerAccess instead of IPC handles. The group's
+// handle is an ipxgpu_ctx without device data; it accepts the entry points KKTSolverDiag needs.
+namespace {
+
+// Runs fn(rank) on one thread per rank; returns the first failure (its message becomes this
+// thread's last error).
+template <class F>
+int group_run(ipxgpu_group* g, F fn) {
+    const int G = (int)g->sub.size();
+    std::vector<int> rc((size_t)G, IPXGPU_OK);
+    std::vector<std::string> msg((size_t)G);
+    std::vector<std::thread> th;
+    for (int r = 0; r < G; r++)
+        th.emplace_back([&, r] {
+            try {
+                rc[r] = fn(r);
+            } catch (const std::bad_alloc&) {
+                rc[r] = fail(IPXGPU_ERR_OUT_OF_MEMORY, "host allocation failed");
+            } catch (const std::exception& e) {
+                rc[r] = fail(IPXGPU_ERR_STATE, e.what());
+            }
+            if (rc[r] != IPXGPU_OK) msg[r] = ipxgpu_last_error();
+        });
+    for (std::thread& t : th) t.join();
+    for (int r = 0; r < G; r++)
+        if (rc[r] != IPXGPU_OK) return fail(rc[r], "rank " + std::to_string(r) + ": " + msg[r]);
+    return IPXGPU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+static void destroy_group(ipxgpu_ctx* c) {
+    ipxgpu_group* g = c->group;
+    for (ipxgpu_ctx* s : g->sub) ipxgpu_destroy(s);
+    delete g;
+    c->group = nullptr;
+    delete c;
+}
+
+int ipxgpu_create_group(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp,
+                        const int64_t* AIi, const double* AIx, const ipxgpu_options* opt_in,
+                        int32_t ngpus, const int32_t* devices) {
+    if (!out) return fail(IPXGPU_ERR_ARGUMENT, "null argument");
+    *out = nullptr;
+    if (ngpus < 2 || ngpus > 16) return fail(IPXGPU_ERR_ARGUMENT, "a group has 2..16 GPUs");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < ngpus)
+        return fail(IPXGPU_ERR_CUDA, "fewer CUDA devices than the group asks for");
+    ipxgpu_options base;
+    ipxgpu_default_options(&base);
+    if (opt_in) base = *opt_in;
+    if (base.stream) return fail(IPXGPU_ERR_ARGUMENT, "a group owns its streams");
+    std::vector<int> dev((size_t)ngpus);
+    for (int r = 0; r < ngpus; r++) {
+        dev[r] = devices ? devices[r] : r;
+        if (dev[r] < 0 || dev[r] >= ndev) return fail(IPXGPU_ERR_ARGUMENT, "device ordinal");
+    }
+    std::vector<int64_t> bounds((size_t)ngpus + 1);
+    IPXGPU_TRY(ipxgpu_partition_columns(n, AIp, ngpus, bounds.data()));
+    char uid[128];
+    IPXGPU_TRY(ipxgpu_comm_unique_id(uid));
+    ipxgpu_group* g = new ipxgpu_group;
+    g->sub.assign((size_t)ngpus, nullptr);
+    int rc = group_run(g, [&](int r) -> int {
+        ipxgpu_options o = base;
+        o.device = dev[r];
+        o.rank = r;
+        o.nranks = ngpus;
+        o.col_begin = bounds[r];
+        o.col_end = bounds[r + 1];
+        IPXGPU_TRY(ipxgpu_create(&g->sub[r], m, n, AIp, AIi, AIx, &o));
+        IPXGPU_TRY(ipxgpu_comm_init(g->sub[r], uid));  // all ranks meet inside NCCL
+        for (int q = 0; q < ngpus; q++)
+            if (q != r) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(dev[q], 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else if (e != cudaSuccess)
+                    return fail(IPXGPU_ERR_CUDA, std::string("peer access: ") + cudaGetErrorString(e));
+            }
+        return ensure_xchg(g->sub[r]);
+    });
+    if (rc == IPXGPU_OK)
+        rc = group_run(g, [&](int r) -> int {
+            ipxgpu_ctx* c = g->sub[r];
+            IPXGPU_TRY(check_ctx(c));
+            for (int q = 0; q < ngpus; q++) c->peer_base[q] = g->sub[q]->xchg;
+            c->peers_direct = true;
+            IPXGPU_TRY(dev_alloc(&c->peer_dev, (size_t)ngpus));
+            IPXGPU_CUDA(cudaMemcpy(c->peer_dev, c->peer_base, sizeof(void*) * ngpus,
+                                   cudaMemcpyHostToDevice));
+            c->peers_ready = true;
+            return IPXGPU_OK;
+        });
+    if (rc != IPXGPU_OK) {
+        const std::string why = ipxgpu_last_error();
+        for (ipxgpu_ctx* s : g->sub) ipxgpu_destroy(s);
+        delete g;
+        return fail(rc, why);
+    }
+    ipxgpu_ctx* lead = new ipxgpu_ctx;
+    lead->group = g;
+    lead->m = m;
+    lead->n = n;
+    lead->nranks = ngpus;
+    lead->device = dev[0];
+    *out = lead;
+    return IPXGPU_OK;
+}
+
+static int group_kktdiag_factorize(ipxgpu_ctx* c, const double* xl, const double* xu,
+                                   const double* zl, const double* zu, double mu, double* W_out,
+                                   double* resscale_out) {
+    ipxgpu_group* g = c->group;
+    return group_run(g, [&](int r) {
+        return ipxgpu_kktdiag_factorize(g->sub[r], xl, xu, zl, zu, mu, W_out, resscale_out);
+    });
+}
+
+namespace {
+// The caller's interrupt callback is polled by rank 0 only; the other ranks follow its verdict,
+// so that all of them stop (the ranks of a solve wait for each other once per iteration).
+struct GroupInterrupt {
+    ipxgpu_interrupt_fn fn;
+    void* user;
+    std::atomic<int64_t> verdict{0};
+};
+int64_t group_interrupt_lead(void* p) {
+    GroupInterrupt* gi = static_cast<GroupInterrupt*>(p);
+    int64_t v = gi->verdict.load();
+    if (v == 0 && gi->fn) {
+        v = gi->fn(gi->user);
+        if (v != 0) gi->verdict.store(v);
+    }
+    return v;
+}
+int64_t group_interrupt_follow(void* p) { return static_cast<GroupInterrupt*>(p)->verdict.load(); }
+}  // namespace
+
+static int group_kktdiag_solve(ipxgpu_ctx* c, const double* a, const double* b, double tol,
+                               int64_t maxiter, double* x, double* y, ipxgpu_cr_result* result,
+                               ipxgpu_interrupt_fn interrupt, void* user) {
+    ipxgpu_group* g = c->group;
+    const int G = (int)g->sub.size();
+    std::vector<ipxgpu_cr_result> res((size_t)G);
+    GroupInterrupt gi;
+    gi.fn = interrupt;
+    gi.user = user;
+    const int rc = group_run(g, [&](int r) {
+        return ipxgpu_kktdiag_solve(g->sub[r], a, b, tol, maxiter, x, y, &res[r],
+                                    r == 0 ? group_interrupt_lead : group_interrupt_follow, &gi);
+    });
+    const int64_t verdict = gi.verdict.load();
+    if (result) {
+        *result = res[0];
+        if (verdict != 0) result->errflag = verdict;
+    }
+    // a rank that stopped on the caller's request leaves its peers waiting for an exchange
+    // that never comes; they give up with an error that is the interrupt's, not a failure
+    if (rc != IPXGPU_OK && verdict != 0) return IPXGPU_OK;
+    return rc;
 }
 
 // ---- host-only layout check ----

@@ -18,8 +18,9 @@ CONFIGS = {
     # basis preconditioning: stop_at_switch = -1, reference src/lp_solver.cc:434-441)
     "C2_diag_phase": (("random", 100_000, 1_000_000, 10, 1002),
                       dict(dualize=0, crossover=0, stop_at_switch=-1)),
-    # configs[3]: transportation LP, full IPM solve (both phases), crossover off
-    "C4_full_ipm": (("transport", 2000, 5000, 1004), dict(dualize=0, crossover=0)),
+    # configs[3]: transportation LP, full IPM solve (both phases) and crossover, so that the
+    # objective compared is that of a vertex (exact up to rounding)
+    "C4_full_ipm": (("transport", 2000, 5000, 1004), dict(dualize=0, crossover=1)),
 }
 
 

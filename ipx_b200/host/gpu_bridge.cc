@@ -26,10 +26,13 @@ struct ModelEntry {
 struct Tables {
     std::mutex mutex;
     std::unordered_map<const ipx::Model*, ModelEntry> models;
+    std::unordered_map<const ipx::Model*, ModelEntry> groups;  // multi-GPU groups (IPXGPU_NGPUS)
     std::unordered_map<const ipx::LinearOperator*, OperatorRecord> operators;
     unsigned long long generation = 0, clock = 0;
     ~Tables() {
         for (auto& kv : models)
+            if (kv.second.ctx) ipxgpu_destroy(kv.second.ctx);
+        for (auto& kv : groups)
             if (kv.second.ctx) ipxgpu_destroy(kv.second.ctx);
     }
 };
@@ -141,6 +144,60 @@ ContextRef CurrentContext(const ipx::Model& model) {
     auto it = t.models.find(&model);
     if (it == t.models.end() || !it->second.ctx) return ContextRef{};
     it->second.last_use = ++t.clock;
+    return ContextRef{it->second.ctx, it->second.generation};
+}
+
+int GroupSize() {
+    static const int g = [] {
+        const char* env = std::getenv("IPXGPU_NGPUS");
+        const long v = env ? std::atol(env) : 1;
+        return (int)(v < 1 ? 1 : (v > 16 ? 16 : v));
+    }();
+    return g;
+}
+
+ContextRef GroupContextFor(const ipx::Model& model) {
+    Tables& t = tables();
+    std::lock_guard<std::mutex> lock(t.mutex);
+    const ipx::SparseMatrix& AI = model.AI();
+    const unsigned long long fp = Fingerprint(AI);
+    auto it = t.groups.find(&model);
+    if (it != t.groups.end()) {
+        ModelEntry& e = it->second;
+        if (e.ctx && e.values == AI.values() && e.entries == AI.entries() &&
+            e.rows == model.rows() && e.cols == model.cols() && e.fingerprint == fp) {
+            e.last_use = ++t.clock;
+            return ContextRef{e.ctx, e.generation};
+        }
+        if (e.ctx) ipxgpu_destroy(e.ctx);
+        t.groups.erase(it);
+    }
+    // one group at a time: a group holds the matrix on every GPU
+    for (auto& kv : t.groups)
+        if (kv.second.ctx) ipxgpu_destroy(kv.second.ctx);
+    t.groups.clear();
+    ipxgpu_options opt;
+    ipxgpu_default_options(&opt);
+    ipxgpu_ctx* ctx = nullptr;
+    Check(ipxgpu_create_group(&ctx, model.rows(), model.cols(), AI.colptr(), AI.rowidx(),
+                              AI.values(), &opt, GroupSize(), nullptr));
+    ModelEntry& e = t.groups[&model];
+    e.ctx = ctx;
+    e.generation = ++t.generation;
+    e.last_use = ++t.clock;
+    e.values = AI.values();
+    e.entries = AI.entries();
+    e.rows = model.rows();
+    e.cols = model.cols();
+    e.fingerprint = fp;
+    return ContextRef{e.ctx, e.generation};
+}
+
+ContextRef CurrentGroupContext(const ipx::Model& model) {
+    Tables& t = tables();
+    std::lock_guard<std::mutex> lock(t.mutex);
+    auto it = t.groups.find(&model);
+    if (it == t.groups.end() || !it->second.ctx) return ContextRef{};
     return ContextRef{it->second.ctx, it->second.generation};
 }
 

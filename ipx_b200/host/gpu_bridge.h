@@ -31,6 +31,16 @@ ContextRef ContextFor(const ipx::Model& model);
 // Cheap lookup by address only; {nullptr, 0} if there is no context.
 ContextRef CurrentContext(const ipx::Model& model);
 
+// Several GPUs behind LpSolver: with IPXGPU_NGPUS = G > 1 in the environment KKTSolverDiag
+// runs on a group of G column-sharded contexts of this process (ipxgpu_create_group: one host
+// thread per GPU for the duration of a call, NVLink peer exchange inside the CR kernels), the
+// diagonal-preconditioned phase being where the column-sharded A*D^2*A' of SURVEY.md
+// section 8e applies. The basis-preconditioned phase keeps the single-GPU context
+// (its triangular solves are sequential, section 8e "not sharded").
+int GroupSize();  // G, or 1
+ContextRef GroupContextFor(const ipx::Model& model);
+ContextRef CurrentGroupContext(const ipx::Model& model);
+
 // Maps a C-ABI return code to IPX's exception convention
 // (reference src/lp_solver.cc:98-105): out of memory -> std::bad_alloc,
 // anything else -> std::runtime_error carrying ipxgpu_last_error().

@@ -30,6 +30,13 @@ namespace {
 int64_t InterruptThunk(void* user) {
     return static_cast<const Control*>(user)->InterruptCheck();
 }
+
+// IPXGPU_NGPUS > 1: the solver runs on a multi-GPU group (gpu_bridge.h). The dense-column
+// preconditioner is a replicated small dense problem and keeps the single-GPU context.
+bool UseGroup(const Control& control, const Model& model) {
+    return ipxb200::GroupSize() > 1 && model.rows() > 0 &&
+           !(control.precond_dense_cols() && model.num_dense_cols() > 0);
+}
 }  // namespace
 
 KKTSolverDiag::KKTSolverDiag(const Control& control, const Model& model)
@@ -54,6 +61,19 @@ void KKTSolverDiag::_Factorize(Iterate* pt, Info* info) {
     };
     iter_ = 0;
     factorized_ = false;
+    if (UseGroup(control_, model_)) {
+        // weights, diagonal and (in _Solve) the whole KKT solve on the group; the member
+        // operators are not primed - nothing outside this class reaches them
+        const ipxb200::ContextRef ref = ipxb200::GroupContextFor(model_);
+        lap("GroupContextFor");
+        Check(ipxgpu_kktdiag_factorize(ref.ctx, pt ? &pt->xl()[0] : nullptr,
+                                       pt ? &pt->xu()[0] : nullptr, pt ? &pt->zl()[0] : nullptr,
+                                       pt ? &pt->zu()[0] : nullptr, pt ? pt->mu() : 0.0, &W_[0],
+                                       &resscale_[0]));
+        lap("ipxgpu_kktdiag_factorize (group)");
+        factorized_ = true;
+        return;
+    }
     {
         const ipxb200::ContextRef ref = ipxb200::ContextFor(model_);
         lap("ContextFor");
@@ -83,7 +103,9 @@ void KKTSolverDiag::_Solve(const Vector& a, const Vector& b, double tol, Vector&
     const Int m = model_.rows();
     const Int n = model_.cols();
     assert(factorized_);
-    const ipxb200::ContextRef ref = ipxb200::CurrentContext(model_);
+    const ipxb200::ContextRef ref = UseGroup(control_, model_)
+                                        ? ipxb200::CurrentGroupContext(model_)
+                                        : ipxb200::CurrentContext(model_);
     if (m == 0) {
         // no constraints: x = W a (reference :108-117 with empty sums)
         for (Int j = 0; j < n; j++) x[j] = W_[j] * a[j];

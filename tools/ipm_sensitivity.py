@@ -22,6 +22,7 @@ ap.add_argument("lp")
 ap.add_argument("--copies", type=int, default=4)
 ap.add_argument("--gpu", action="store_true", help="also run the drop-in build on the unperturbed LP")
 ap.add_argument("--out", default=None)
+ap.add_argument("--golden", default=None, help="write the compact fixture the tests read")
 args = ap.parse_args()
 kind, *dims = args.lp.split(":")
 d = [int(v) for v in dims]
@@ -56,3 +57,19 @@ for k in range(depth):
 if args.out:
     with open(args.out, "w") as f:
         json.dump({"lp": lp.name, "runs": runs}, f, indent=1)
+if args.golden:
+    # compact form for tests/golden: the reference runs only, and the number of leading
+    # iterations on which all of them print the same table row
+    refs = [runs[n] for n in names if n.startswith("ref")]
+    stable = 0
+    key = lambda row: row["kktiter"]  # the printed residuals differ in the 3rd digit by iteration 2
+    while all(len(r["per_iter"]) > stable for r in refs) and all(
+            key(r["per_iter"][stable]) == key(refs[0]["per_iter"][stable]) for r in refs):
+        stable += 1
+    with open(args.golden, "w") as f:
+        json.dump({"lp": lp.name, "perturbation": "rhs and obj entrywise times (1 + e * 2^-52), "
+                   "e in {-1, 0, 1}; first run unperturbed", "stable_iterations": stable,
+                   "stable_iterations_meaning": "leading IPM iterations on which all runs need the "
+                   "same number of CR iterations",
+                   "runs": [{k: r[k] for k in ("status", "status_ipm", "iter", "kktiter1", "pobjval",
+                                                "dobjval", "per_iter")} for r in refs]}, f, indent=1)
