@@ -320,6 +320,27 @@ mul_sub_kernel(long long n, const double* __restrict__ a, const double* __restri
         out[j] = __dmul_rn(a[j], b[j]) - c[j];
 }
 
+// The normal matrix of a model without structural columns is diag(W_slack) (reference
+// src/normal_matrix.cc:65-66 with an empty column loop): y = Ws .* x, y[m] = x'y, then the scalar
+// step of the CR loop. One CTA.
+__global__ void __launch_bounds__(kBlock)
+slack_apply_kernel(int m, const double* __restrict__ Ws, const double* __restrict__ x,
+                   double* __restrict__ y, int mode, int slot, CrState* st) {
+    __shared__ double s_red[kWarps];
+    if (st != nullptr && st->done) return;
+    double dot = 0.0;
+    for (int i = threadIdx.x; i < m; i += kBlock) {
+        const double yi = Ws ? __dmul_rn(x[i], Ws[i]) : 0.0;
+        y[i] = yi;
+        dot += __dmul_rn(x[i], yi);
+    }
+    const double tot = block_sum(dot, s_red);
+    if (threadIdx.x == 0) {
+        y[m] = tot;
+        if (st && !(mode == kApplyPlain && slot == kSlotNone)) after_apply(st, mode, tot, slot);
+    }
+}
+
 // x = a - x
 __global__ void __launch_bounds__(kBlock)
 sub_from_kernel(long long n, const double* __restrict__ a, double* x) {

@@ -188,7 +188,15 @@ static int launch_normal_apply_w(ipxgpu_ctx* c, const double* Wc, const double* 
                                  const double* x, double* y, int mode, int slot, CrState* st) {
     const int np = (int)c->panels.size();
     const bool sharded = c->nranks > 1;
-    if (np == 0 || c->m == 0) return IPXGPU_OK;
+    if (c->m == 0) return IPXGPU_OK;
+    if (np == 0) {
+        // no structural columns here: C = diag(W_slack)
+        if (sharded) return fail(IPXGPU_ERR_UNSUPPORTED, "a column shard without columns");
+        slack_apply_kernel<<<1, kBlock, 0, c->stream>>>((int)c->m, Ws, x, y, mode, slot, st);
+        c->launches++;
+        IPXGPU_CUDA(cudaGetLastError());
+        return IPXGPU_OK;
+    }
     const bool band1 = band_usable(c->band1, x), band2 = band_usable(c->band2, c->t);
     if (band1) {
         BandArgs a1{x, Wc, nullptr, nullptr, c->t, kApplyPlain, kSlotNone};

@@ -8,9 +8,13 @@
 #include <cmath>
 #include <vector>
 
+// Hidden visibility: these three cover only what IPX calls; an application that also loads a
+// real LAPACK (HiGHS, numpy ...) must neither pick them up nor have its own interposed here.
+#define IPX_LAPACK_LOCAL __attribute__((visibility("hidden")))
+
 extern "C" {
 
-void dpotrf_(const char* uplo, const int* n, double* a, const int* lda,
+IPX_LAPACK_LOCAL void dpotrf_(const char* uplo, const int* n, double* a, const int* lda,
              int* info) {
     const int N = *n, LDA = *lda;
     *info = 0;
@@ -33,7 +37,7 @@ void dpotrf_(const char* uplo, const int* n, double* a, const int* lda,
     }
 }
 
-void dpotrs_(const char* uplo, const int* n, const int* nrhs, const double* a,
+IPX_LAPACK_LOCAL void dpotrs_(const char* uplo, const int* n, const int* nrhs, const double* a,
              const int* lda, double* b, const int* ldb, int* info) {
     const int N = *n, LDA = *lda, LDB = *ldb;
     *info = 0;
@@ -55,7 +59,7 @@ void dpotrs_(const char* uplo, const int* n, const int* nrhs, const double* a,
 
 // Reciprocal condition number of a lower triangular matrix in the 1-norm,
 // computed from the explicit inverse (O(n^3); n <= 1000 dense columns).
-void dtrcon_(const char* norm, const char* uplo, const char* diag, const int* n,
+IPX_LAPACK_LOCAL void dtrcon_(const char* norm, const char* uplo, const char* diag, const int* n,
              const double* a, const int* lda, double* rcond, double* work,
              int* iwork, int* info) {
     (void)norm; (void)work; (void)iwork;

@@ -9,9 +9,10 @@ runs the diagonal-preconditioned phase only, which ENDS where the CR method stop
 (reference src/lp_solver.cc:386-394): there the reference's own path is not determined to
 +-1 iteration - one-ulp perturbations of rhs and objective move it between 21 and 22 iterations
 and the objective by 1e-5 relative (tests/golden/e2e_C2_sensitivity.json, from
-tools/ipm_sensitivity.py) - so the bar there is: the same CR iteration counts until the paths
-part ways (five iterations), then iteration count and objective inside the band the perturbed
-reference runs span, widened by one iteration / by the band's own width.
+tools/ipm_sensitivity.py) - so the bar there is: the same CR iteration counts while the arms
+still agree to rounding (two rows of the iteration table), then per-row CR counts, iteration
+count and objective inside the band the reference's own runs span (ulp copies and column
+orders), widened by one iteration / by the band's own width.
 """
 
 import json
@@ -41,18 +42,21 @@ def test_config2_diagonal_phase_full_size(gpulib):
     lp = e2e.make_lp(spec)
     got = e2e.solve(gpulib, lp, per_iter=True, **params)
     assert got["status"] == ref["status"] and got["status_ipm"] == ref["status_ipm"]
-    # the first iterations, on which every perturbed reference run needs the same number of CR
-    # iterations: so does the device arm, and its mu lies in the band those runs span (already
-    # 0.3 % wide after two iterations), widened by the band's own width
+    # Rows 0 and 1 of the iteration table: the arms agree to rounding there, so the CR counts
+    # are the reference's. From row 2 on a row's CR count depends on the summation order (of 24
+    # column orders of the reference 23 need 42 iterations in row 2 and one needs 41): the
+    # device arm must stay within the reference runs' range widened by two (by a tenth late in the
+    # phase, where a solve takes 150-200 iterations).
     stable = sens["stable_iterations"]
-    assert stable >= 4
+    assert stable >= 2
     for k in range(stable):
-        want = [r["per_iter"][k] for r in sens["runs"]]
-        b = got["per_iter"][k]
-        assert b["kktiter"] == want[0]["kktiter"], (k, b, want[0])
-        lo, hi = min(w["mu"] for w in want), max(w["mu"] for w in want)
-        slack = (hi - lo) + 0.005 * hi  # + the last printed digit
-        assert lo - slack <= b["mu"] <= hi + slack, (k, b["mu"], lo, hi)
+        assert got["per_iter"][k]["kktiter"] == ref["per_iter"][k]["kktiter"], k
+        assert got["per_iter"][k]["mu"] == ref["per_iter"][k]["mu"], k
+    common = min(len(r["per_iter"]) for r in sens["runs"])
+    for k in range(stable, min(common, len(got["per_iter"]))):
+        want = [r["per_iter"][k]["kktiter"] for r in sens["runs"]]
+        lo, hi = min(want) - max(2, min(want) // 10), max(want) + max(2, max(want) // 10)
+        assert lo <= got["per_iter"][k]["kktiter"] <= hi, (k, got["per_iter"][k]["kktiter"], want)
     iters = [r["iter"] for r in sens["runs"]]
     objs = [r["pobjval"] for r in sens["runs"]]
     crs = [r["kktiter1"] for r in sens["runs"]]

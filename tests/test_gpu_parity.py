@@ -459,3 +459,25 @@ def test_sharded_solve_over_nvlink_peer_memory(exchange):
                         "--master-port", "29517", os.path.join(repo, "tools", "check_sharded.py")],
                        capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0 and "SHARDED PARITY PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_model_without_structural_columns():
+    """n = 0: AI is the identity, C = diag(W) (reference src/normal_matrix.cc:65-66 with an empty
+    column loop); apply, diagonal and a preconditioned CR solve."""
+    m = 50
+    AIp = np.arange(m + 1, dtype=np.int64)
+    AIi = np.arange(m, dtype=np.int64)
+    AIx = np.ones(m)
+    ctx = capi.Context(m, 0, AIp, AIi, AIx)
+    W = lpgen.weights(m, "mid", 3)
+    x = np.random.default_rng(4).standard_normal(m)
+    ctx.normal_prepare(W)
+    y, dot = ctx.normal_apply(x)
+    assert np.array_equal(y, W * x)
+    assert abs(dot - x @ (W * x)) <= 1e-13 * np.abs(x * W * x).sum()
+    ctx.diag_factorize(W)
+    assert np.array_equal(ctx.diag_get(), W)
+    z, info = ctx.pcr_solve(x, 1e-12, None, -1)
+    assert info["errflag"] == 0 and info["iter"] <= 2
+    assert np.abs(W * z - x).max() <= 1e-12 * np.abs(x).max()
+    ctx.close()

@@ -20,6 +20,12 @@ from ipx_b200 import e2e, ipxlib, lpgen  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("lp")
 ap.add_argument("--copies", type=int, default=4)
+ap.add_argument("--mode", default="ulp", choices=["ulp", "permute"],
+                help="ulp: rhs and obj times (1 +- 2^-52); permute: the SAME LP with its columns in "
+                     "a random order - every sum over columns inside the reference (A*W*A' applies, "
+                     "right-hand sides, recoveries) is then taken in another order, which is the "
+                     "kind of difference a device arm has in every operator apply")
+ap.add_argument("--seed", type=int, default=5)
 ap.add_argument("--gpu", action="store_true", help="also run the drop-in build on the unperturbed LP")
 ap.add_argument("--out", default=None)
 ap.add_argument("--golden", default=None, help="write the compact fixture the tests read")
@@ -32,8 +38,23 @@ params = dict(dualize=0, crossover=0, stop_at_switch=-1)
 ref = ipxlib.IpxLibrary(ipxlib.REF_LIB)
 runs = {}
 runs["ref"] = e2e.solve(ref, lp, per_iter=True, **params)
-rng = np.random.default_rng(5)
+rng = np.random.default_rng(args.seed)
+def permuted(lp, perm):
+    """The same LP with column perm[k] at position k."""
+    cnt = np.diff(lp.Ap)[perm]
+    Ap = np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+    src = (np.repeat(lp.Ap[:-1][perm], cnt) + np.arange(int(Ap[-1])) - np.repeat(Ap[:-1], cnt))
+    q = lpgen.LP(**{**lp.__dict__})
+    q.Ap, q.Ai, q.Ax = Ap, lp.Ai[src], lp.Ax[src]
+    q.obj, q.lb, q.ub = lp.obj[perm], lp.lb[perm], lp.ub[perm]
+    return q
+
+
 for c in range(args.copies):
+    if args.mode == "permute":
+        q = permuted(lp, rng.permutation(lp.n))
+        runs[f"ref+perm{c}"] = e2e.solve(ref, q, per_iter=True, **params)
+        continue
     q = lpgen.LP(**{**lp.__dict__})
     ulp = 2.0 ** -52
     q.rhs = lp.rhs * (1.0 + ulp * rng.choice(np.array([-1.0, 0.0, 1.0]), lp.m))
@@ -67,8 +88,10 @@ if args.golden:
             key(r["per_iter"][stable]) == key(refs[0]["per_iter"][stable]) for r in refs):
         stable += 1
     with open(args.golden, "w") as f:
-        json.dump({"lp": lp.name, "perturbation": "rhs and obj entrywise times (1 + e * 2^-52), "
-                   "e in {-1, 0, 1}; first run unperturbed", "stable_iterations": stable,
+        json.dump({"lp": lp.name, "perturbation": ("the same LP with its columns in random orders; first run "
+                                    "in the generator's order" if args.mode == "permute" else
+                                    "rhs and obj entrywise times (1 + e * 2^-52), e in {-1, 0, 1}; "
+                                    "first run unperturbed"), "stable_iterations": stable,
                    "stable_iterations_meaning": "leading IPM iterations on which all runs need the "
                    "same number of CR iterations",
                    "runs": [{k: r[k] for k in ("status", "status_ipm", "iter", "kktiter1", "pobjval",
