@@ -461,7 +461,7 @@ def test_sharded_solve_over_nvlink_peer_memory(exchange):
     assert r.returncode == 0 and "SHARDED PARITY PASS" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
-def test_model_without_structural_columns():
+def test_model_without_structural_columns(capi):
     """n = 0: AI is the identity, C = diag(W) (reference src/normal_matrix.cc:65-66 with an empty
     column loop); apply, diagonal and a preconditioned CR solve."""
     m = 50
