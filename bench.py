@@ -144,7 +144,7 @@ def cpu_reference_rate(lp, W, rhs, resscale, iters, reps):
     """CR applies/s of the reference's CPU code (NormalMatrix + DiagonalPrecond +
     ConjugateResiduals from oracle/_ref), or of the oracle port if that build is
     absent. One core: the reference has no threading."""
-    from ipx_b200 import ipxlib
+    from oracle import ipxlib
     if os.path.exists(ipxlib.REF_LIB):
         ref = ipxlib.IpxLibrary(ipxlib.REF_LIB)
         mdl = ref.model(lp)
@@ -203,30 +203,23 @@ def run_reference(args):
                 "d2h_bytes_per_step": 0},
     }
     if not args.no_ipm and not STRONG:
-        from ipx_b200 import ipxlib
+        from oracle import ipxlib
         if os.path.exists(ipxlib.REF_LIB):
             line["e2e_ipm"] = ipm_diag_phase(ipxlib.REF_LIB, lp)
     print(json.dumps(line), flush=True)
 
 
 def ipm_diag_phase(lib_path, lp):
-    """End-to-end IPM solve through ipx_c.h: the diagonal-preconditioned phase of the LP
-    (stop_at_switch = -1: IPX stops where it would switch to basis preconditioning, no
-    crossover). Returns the ipx_info fields BASELINE.json's second metric needs."""
-    from ipx_b200 import ipxlib
-    lib = ipxlib.IpxLibrary(lib_path)
-    s = lib.lp_solver()
-    s.set_parameters(display=0, dualize=0, crossover=0, stop_at_switch=-1)
-    assert s.load_model(lp) == 0
-    t0 = time.perf_counter()
-    s.solve()
-    wall = time.perf_counter() - t0
-    info = s.info()
-    s.close()
+    """End-to-end IPM solve through ipx_c.h (ipx_b200/ipxc.py binds nothing but that API): the
+    diagonal-preconditioned phase of the LP (stop_at_switch = -1: IPX stops where it would
+    switch to basis preconditioning, no crossover). Returns the ipx_info fields BASELINE.json's
+    second metric needs."""
+    from ipx_b200 import e2e, ipxc
+    res = e2e.solve(ipxc.IpxC(lib_path), lp, dualize=0, crossover=0, stop_at_switch=-1)
     keys = ("status status_ipm iter kktiter1 time_total time_ipm1 time_kkt_factorize "
             "time_kkt_solve time_cr1 time_cr1_AAt time_cr1_pre pobjval dobjval").split()
-    out = {k: info[k] for k in keys}
-    out["wall_s"] = wall
+    out = {k: res[k] for k in keys}
+    out["wall_s"] = res["wall"]
     out["workload"] = (f"{lp.name}: diagonal-preconditioned IPM phase (KKTSolverDiag, "
                        "stop_at_switch = -1, no crossover), ipx_c.h API")
     return out
@@ -600,8 +593,8 @@ def run_gpu(args):
             "sample": "2 CR solves x 10 applies of the same 100k x 1M LP on one host core "
                       f"(the reference is single-threaded; box has {os.cpu_count()} cores)"}
     if rank == 0 and world == 1 and not args.no_ipm and not STRONG:
-        from ipx_b200 import ipxlib
-        line["e2e_ipm"] = ipm_diag_phase(ipxlib.GPU_LIB, lp)
+        from ipx_b200 import ipxc
+        line["e2e_ipm"] = ipm_diag_phase(ipxc.GPU_LIB, lp)
     failed = False
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -27,7 +27,7 @@ LIBIPX_GPU = os.path.join(OUT, "libipx_gpu.so")
 REPLACED = ["normal_matrix", "diagonal_precond", "conjugate_residuals", "splitted_normal_matrix",
             "kkt_solver_diag", "kkt_solver_basis"]
 ABSENT = ["basiclu_wrapper", "basiclu_kernel"]  # need the un-vendored BASICLU
-SHIMS = ["lu_provider", "sparse_lu", "lapack_min", "ipx_harness"]
+SHIMS = ["lu_provider", "sparse_lu", "lapack_min"]
 
 
 def _newer(target, sources):

@@ -1,5 +1,5 @@
-"""End-to-end LP solves through the unchanged ipx_c.h API of an IPX build (the reference's CPU
-build oracle/_ref/libipx_ref.so or the drop-in build ipx_b200/_build/libipx_gpu.so), with the
+"""End-to-end LP solves through the unchanged ipx_c.h API of an IPX build (the drop-in build
+ipx_b200/_build/libipx_gpu.so, or the reference's own CPU build when a test passes it in), with the
 per-iteration table of IPM::PrintOutput (reference src/ipm.cc:659-678) parsed from the log."""
 
 import os
@@ -56,7 +56,7 @@ def parse_log(path):
 
 
 def solve(lib, lp, per_iter=False, display=0, **params):
-    """Solves lp with the IPX build `lib` (ipxlib.IpxLibrary); returns the ipx_info fields, the
+    """Solves lp with the IPX build `lib` (anything with lp_solver(): ipxc.IpxC, or the test harness's loader); returns the ipx_info fields, the
     wall time and, with per_iter, the iteration table."""
     s = lib.lp_solver()
     logpath = logbytes = None

@@ -13,7 +13,7 @@
 //    (src/forrest_tomlin.h) running on that kernel. BasicLu's layout is fixed
 //    by the header, so the delegate lives in a side table keyed by `this`.
 //
-// It is linked into BOTH the CPU reference build (oracle/_ref) and the GPU
+// It is linked into BOTH the CPU reference build of the test suite and the GPU
 // drop-in build, so the two arms see identical L, U and permutations.
 
 #include <memory>

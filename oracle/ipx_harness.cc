@@ -1,12 +1,13 @@
 // C entry points over IPX's own operator / KKT-solver classes.
 //
-// This TU is compiled against the UNMODIFIED reference headers and linked into
-// two shared libraries that export the same symbols:
-//   oracle/_ref/libipx_ref.so   reference CPU objects (the parity oracle and
-//                               the CPU baseline), and
-//   ipx_b200/_build/libipx_gpu.so  the same reference objects EXCEPT the six
-//                               hot-path TUs, which are replaced by the GPU
-//                               drop-ins in this directory.
+// TEST INFRASTRUCTURE. This TU is compiled against the UNMODIFIED reference headers and
+// linked into two shared libraries that export the same symbols:
+//   oracle/_ref/libipx_ref.so          with the reference CPU objects (the parity oracle
+//                                      and the CPU baseline), and
+//   oracle/_ref/libipx_gpu_harness.so  alone, against ipx_b200/_build/libipx_gpu.so - the
+//                                      same reference objects EXCEPT the six hot-path TUs,
+//                                      which are replaced by the GPU drop-ins of
+//                                      ipx_b200/host. The product library holds no test code.
 // Tests drive both through identical calls, so a parity test reads like a test
 // of the reference's own classes (NormalMatrix::Apply, DiagonalPrecond::
 // Factorize/Apply, ConjugateResiduals::Solve, KKTSolverDiag, Basis,

@@ -1,14 +1,15 @@
-"""ctypes bindings for a built IPX shared library.
+"""ctypes bindings of the TEST HARNESS (oracle/ipx_harness.cc) over a built IPX.
 
-Two libraries export the same symbols (ipx_b200/host/ipx_harness.cc plus the
-unchanged reference C API, reference include/ipx_c.h:13-62):
+Two libraries export the same harness symbols next to the unchanged reference C API
+(reference include/ipx_c.h:13-62):
 
-* ``oracle/_ref/libipx_ref.so``     - the reference's own CPU code (oracle / CPU baseline)
-* ``ipx_b200/_build/libipx_gpu.so`` - the same with the hot-path TUs replaced by the
-  GPU drop-ins
+* ``oracle/_ref/libipx_ref.so``          - the reference's own CPU code (oracle / CPU baseline),
+  harness linked in
+* ``oracle/_ref/libipx_gpu_harness.so``  - the harness alone, linked AGAINST the product
+  ``ipx_b200/_build/libipx_gpu.so`` (the drop-in build; it contains no test code)
 
-so a test drives both through the same calls. This module is harness code, not
-part of the product path.
+so a test drives IPX's own classes on both arms through the same calls. Test infrastructure:
+only tests/, tools/ and bench.py's reference legs import this module.
 """
 
 import ctypes as C
@@ -16,80 +17,20 @@ import os
 
 import numpy as np
 
-ipxint = C.c_int64
+from ipx_b200.ipxc import (Info, LpSolver, Parameters, _d, _f64, _i, _i64,  # noqa: F401
+                           declare_c_api, ipxint)
+
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int64)
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_LIB = os.path.join(REPO, "oracle", "_ref", "libipx_ref.so")
-GPU_LIB = os.path.join(REPO, "ipx_b200", "_build", "libipx_gpu.so")
-
-
-class Parameters(C.Structure):
-    """struct ipx_parameters (reference include/ipx_parameters.h:6-50)."""
-    _fields_ = [
-        ("display", ipxint), ("logfile", C.c_char_p), ("print_interval", C.c_double),
-        ("time_limit", C.c_double), ("dualize", ipxint), ("scale", ipxint),
-        ("ipm_maxiter", ipxint), ("ipm_feasibility_tol", C.c_double),
-        ("ipm_optimality_tol", C.c_double), ("ipm_drop_primal", C.c_double),
-        ("ipm_drop_dual", C.c_double), ("kkt_tol", C.c_double),
-        ("precond_dense_cols", ipxint), ("crash_basis", ipxint),
-        ("dependency_tol", C.c_double), ("volume_tol", C.c_double),
-        ("rows_per_slice", ipxint), ("maxskip_updates", ipxint), ("lu_kernel", ipxint),
-        ("lu_pivottol", C.c_double), ("crossover", ipxint), ("crossover_start", C.c_double),
-        ("pfeasibility_tol", C.c_double), ("dfeasibility_tol", C.c_double),
-        ("debug", ipxint), ("switchiter", ipxint), ("stop_at_switch", ipxint),
-        ("update_heuristic", ipxint), ("maxpasses", ipxint),
-    ]
-
-
-_INFO_INT = ("status status_ipm status_crossover errflag num_var num_constr num_entries "
-             "num_rows_solver num_cols_solver num_entries_solver dualized dense_cols "
-             "dependent_rows dependent_cols rows_inconsistent cols_inconsistent "
-             "primal_dropped dual_dropped").split()
-_INFO_DBL1 = ("abs_presidual abs_dresidual rel_presidual rel_dresidual pobjval dobjval "
-              "rel_objgap complementarity normx normy normz objval primal_infeas "
-              "dual_infeas").split()
-_INFO_INT2 = ("iter kktiter1 kktiter2 basis_repairs updates_start updates_ipm "
-              "updates_crossover").split()
-_INFO_DBL2 = ("time_total time_ipm1 time_ipm2 time_starting_basis time_crossover "
-              "time_kkt_factorize time_kkt_solve time_maxvol time_cr1 time_cr1_AAt "
-              "time_cr1_pre time_cr2 time_cr2_NNt time_cr2_B time_cr2_Bt ftran_sparse "
-              "btran_sparse time_ftran time_btran time_lu_invert time_lu_update mean_fill "
-              "max_fill time_symb_invert").split()
-_INFO_INT3 = "maxvol_updates maxvol_skipped maxvol_passes tbl_nnz".split()
-_INFO_DBL3 = "tbl_max frobnorm_squared lambdamax volume_increase".split()
-
-
-class Info(C.Structure):
-    """struct ipx_info (reference include/ipx_info.h:6-100)."""
-    _fields_ = ([(k, ipxint) for k in _INFO_INT] + [(k, C.c_double) for k in _INFO_DBL1] +
-                [(k, ipxint) for k in _INFO_INT2] + [(k, C.c_double) for k in _INFO_DBL2] +
-                [(k, ipxint) for k in _INFO_INT3] + [(k, C.c_double) for k in _INFO_DBL3])
-
-    def asdict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+GPU_LIB = os.path.join(REPO, "oracle", "_ref", "libipx_gpu_harness.so")
 
 
 INFO_OUT_KEYS = ("errflag kktiter1 kktiter2 time_cr1 time_cr1_AAt time_cr1_pre time_cr2 "
                  "time_cr2_NNt time_cr2_B time_cr2_Bt time_kkt_factorize time_kkt_solve "
                  "updates_ipm primal_dropped dual_dropped time_maxvol").split()
-
-
-def _d(a):
-    return None if a is None else a.ctypes.data_as(_dp)
-
-
-def _i(a):
-    return None if a is None else a.ctypes.data_as(_ip)
-
-
-def _f64(a):
-    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
-
-
-def _i64(a):
-    return None if a is None else np.ascontiguousarray(a, dtype=np.int64)
 
 
 class IpxLibrary:
@@ -107,12 +48,9 @@ class IpxLibrary:
         for name in ("ipxh_diag_factorize", "ipxh_kktdiag_factorize", "ipxh_kktdiag_solve",
                      "ipxh_kktdiag_iter", "ipxh_basis_load", "ipxh_basis_from_weights",
                      "ipxh_kktbasis_factorize", "ipxh_kktbasis_solve",
-                     "ipxh_triangular_solve", "ipx_load_model", "ipx_solve",
-                     "ipx_get_interior_solution", "ipx_get_basic_solution"):
+                     "ipxh_triangular_solve"):
             getattr(L, name).restype = ipxint
-        L.ipx_default_parameters.restype = Parameters
-        L.ipx_get_parameters.restype = Parameters
-        L.ipx_get_info.restype = Info
+        declare_c_api(L)  # the public API, from the same handle (the drop-in build is a dependency)
 
     def default_parameters(self):
         return self.lib.ipx_default_parameters()
@@ -326,51 +264,3 @@ class IpxModel:
         err = self.lib.ipxh_kktbasis_solve(self.h, _d(a), _d(b), C.c_double(tol), _d(x), _d(y),
                                            _d(out))
         return x, y, dict(zip(INFO_OUT_KEYS, out.tolist()), err=err)
-
-
-class LpSolver:
-    """ipx::LpSolver through the unchanged C API (reference include/ipx_c.h)."""
-
-    def __init__(self, ipxlib):
-        self.lib = ipxlib.lib
-        self.h = C.c_void_p()
-        self.lib.ipx_new(C.byref(self.h))
-        self.num_var = self.num_constr = 0
-
-    def close(self):
-        if self.h:
-            self.lib.ipx_free(C.byref(self.h))
-
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
-
-    def set_parameters(self, **params):
-        p = self.lib.ipx_get_parameters(self.h)
-        for k, v in params.items():
-            setattr(p, k, v)
-        self.lib.ipx_set_parameters(self.h, p)
-
-    def load_model(self, lp):
-        self._keep = [_i64(lp.Ap), _i64(lp.Ai), _f64(lp.Ax), _f64(lp.rhs), _f64(lp.obj),
-                      _f64(lp.lb), _f64(lp.ub)]
-        Ap, Ai, Ax, rhs, obj, lb, ub = self._keep
-        self.num_var, self.num_constr = lp.n, lp.m
-        return self.lib.ipx_load_model(self.h, ipxint(lp.n), _d(obj), _d(lb), _d(ub), ipxint(lp.m),
-                                       _i(Ap), _i(Ai), _d(Ax), _d(rhs), C.c_char_p(lp.constr_type))
-
-    def solve(self):
-        return self.lib.ipx_solve(self.h)
-
-    def info(self):
-        return self.lib.ipx_get_info(self.h).asdict()
-
-    def interior_solution(self):
-        n, m = self.num_var, self.num_constr
-        x, xl, xu, zl, zu = (np.empty(n) for _ in range(5))
-        slack, y = np.empty(m), np.empty(m)
-        err = self.lib.ipx_get_interior_solution(self.h, _d(x), _d(xl), _d(xu), _d(slack), _d(y),
-                                                 _d(zl), _d(zu))
-        return err, dict(x=x, xl=xl, xu=xu, slack=slack, y=y, zl=zl, zu=zu)

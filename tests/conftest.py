@@ -24,7 +24,7 @@ def oracle():
 @pytest.fixture(scope="session")
 def reflib():
     """The compiled reference (oracle/_ref/libipx_ref.so) when it is present."""
-    from ipx_b200 import ipxlib
+    from oracle import ipxlib
     if not os.path.exists(ipxlib.REF_LIB):
         pytest.skip("oracle/_ref/libipx_ref.so not built (needs /root/reference)")
     return ipxlib.IpxLibrary(ipxlib.REF_LIB)
@@ -33,7 +33,7 @@ def reflib():
 @pytest.fixture(scope="session")
 def gpulib():
     """IPX with the GPU drop-ins (ipx_b200/_build/libipx_gpu.so)."""
-    from ipx_b200 import ipxlib
+    from oracle import ipxlib
     if not os.path.exists(ipxlib.GPU_LIB):
         pytest.fail("ipx_b200/_build/libipx_gpu.so missing: run __graft_entry__.build()")
     return ipxlib.IpxLibrary(ipxlib.GPU_LIB)

@@ -14,7 +14,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
-from ipx_b200 import e2e, ipxlib  # noqa: E402
+from ipx_b200 import e2e
+from oracle import ipxlib  # noqa: E402
 
 if __name__ == "__main__":
     names = sys.argv[1:] or sorted(e2e.CONFIGS)

@@ -18,7 +18,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
-from ipx_b200 import ipxlib, lpgen  # noqa: E402
+from ipx_b200 import lpgen
+from oracle import ipxlib  # noqa: E402
 
 
 def cases():

@@ -62,6 +62,7 @@ def test_product_code_never_touches_the_oracle():
                 s = line.strip()
                 if s.startswith(("#", "//", "*", '"""')):
                     continue
-                if re.search(r"(import\s+oracle|from\s+oracle|liboracle|ipx_oracle\.h|pyoracle)", s):
+                if re.search(r"(import\s+oracle|from\s+oracle|liboracle|ipx_oracle\.h|pyoracle|"
+                             r"[\"']oracle[\"']|oracle/|ipx_harness|libipx_ref)", s):
                     bad.append((f, s))
     assert not bad, bad

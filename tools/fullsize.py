@@ -279,7 +279,8 @@ def main():
     args = ap.parse_args()
     if not args.configs and not args.basis:
         args.configs = ["C2"]
-    from ipx_b200 import capi, ipxlib
+    from ipx_b200 import capi
+    from oracle import ipxlib
     from oracle import pyoracle
     capi.load()
     pyoracle.lib()

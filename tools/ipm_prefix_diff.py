@@ -9,7 +9,8 @@ import sys
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from ipx_b200 import ipxlib, lpgen  # noqa: E402
+from ipx_b200 import lpgen
+from oracle import ipxlib  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("lp")

@@ -8,7 +8,8 @@ import sys
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from ipx_b200 import e2e, ipxlib, lpgen  # noqa: E402
+from ipx_b200 import e2e, lpgen
+from oracle import ipxlib  # noqa: E402
 
 
 

@@ -23,7 +23,7 @@ args = ap.parse_args()
 
 if args.make:
     from tools.fullsize import make_lp
-    from ipx_b200 import ipxlib
+    from oracle import ipxlib
     ref = ipxlib.IpxLibrary(ipxlib.REF_LIB)
     lp = make_lp("C3", args.scale)
     mdl = ref.model(lp, dualize=0)
