@@ -348,8 +348,11 @@ static int run_cr_fused(ipxgpu_ctx* c, bool precond, bool zero_start, bool use_r
     const int m = (int)c->m;
     const char* trace_env = std::getenv("IPXGPU_FUSED_TRACE");
     const bool item_trace = trace_env && std::atoi(trace_env) == 2;
-    auto kernel = item_trace ? pcr_fused_kernel<kBandWarps, kBandDepth, 4>
-                             : pcr_fused_kernel<kBandWarps, kBandDepth, 0>;
+    const bool sharded = c->nranks > 1;
+    auto kernel = item_trace ? (sharded ? pcr_fused_kernel<kBandWarps, kBandDepth, 4, 1>
+                                        : pcr_fused_kernel<kBandWarps, kBandDepth, 4, 0>)
+                             : (sharded ? pcr_fused_kernel<kBandWarps, kBandDepth, 0, 1>
+                                        : pcr_fused_kernel<kBandWarps, kBandDepth, 0, 0>);
     const size_t smem = std::max(c->band1->plan.smem, c->band2->plan.smem);
     const int threads = (kBandWarps + 1) * 32;
     IPXGPU_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -419,6 +422,9 @@ static int run_cr_fused(ipxgpu_ctx* c, bool precond, bool zero_start, bool use_r
         const std::string how = env ? env : "auto";
         F.xll_off = how == "pull" ? 0 : c->xchg_ll_off;
         F.xtwo_phase = how == "two" || (how != "one" && c->nranks >= 4);
+        // IPXGPU_XFOLD=0: grid barrier after sweep 2 and the exchange as a stage of its own
+        const char* fold = std::getenv("IPXGPU_XFOLD");
+        F.xfold = !(fold && std::atoi(fold) == 0);
     }
     F.t = c->t;
     F.zero_start = zero_start ? 1 : 0;

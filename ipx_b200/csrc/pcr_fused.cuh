@@ -69,6 +69,7 @@ struct FusedArgs {
     // every rank's buffer, followed by final[2][xmpad]; 0 = pull exchange (flags + P2P loads).
     size_t xll_off;
     int xtwo_phase;  // reduce-scatter + all-gather of records instead of all-to-all
+    int xfold;       // sharded: exchange a row block's rows right after its sweep-2 items (no grid barrier)
 };
 
 // 16-byte record of two self-validating 64-bit words {generation | half of the value}: 64-bit
@@ -89,6 +90,21 @@ __device__ __forceinline__ bool xll_load(const ulonglong2* p, unsigned gen, doub
                  : "memory");
     *val = __longlong_as_double((long long)(((w1 & 0xffffffffull) << 32) | (w0 & 0xffffffffull)));
     return (unsigned)(w0 >> 32) == gen && (unsigned)(w1 >> 32) == gen;
+}
+
+// Waits for a record of generation gen; a peer that never arrives must not hang this GPU: after
+// 2^24 polls (or when another thread gave up) the abort word is raised and the wait ends.
+__device__ __forceinline__ void xchg_wait(const ulonglong2* p, unsigned gen, double* val,
+                                       double* abort_word) {
+    long long spins = 0;
+    while (!xll_load(p, gen, val)) {
+        if ((++spins & 0xffff) == 0) {
+            if (spins > (1ll << 24) || __ldcg(abort_word) != 0.0) {
+                *abort_word = 2.0;
+                break;
+            }
+        }
+    }
 }
 
 constexpr int kFusedStages = 6;
@@ -192,9 +208,12 @@ __device__ __forceinline__ void fused_block_reduce(double* s_red, double& a, dou
     }
 }
 
-template <int NW, int D, int DBG = 0>
+// SH = 0: the single-shard kernel (no exchange code compiled in: the 64-register budget of a
+// 1024-thread CTA is tight); SH = 1: column shards.
+template <int NW, int D, int DBG = 0, int SH = 0>
 __global__ void __launch_bounds__((NW + 1) * 32, 1)
 pcr_fused_kernel(FusedArgs F) {
+    const int nranks = SH ? F.nranks : 1;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double s_red[96];
     __shared__ double s_bcast[4 + 3 * kMaxGridSync];
@@ -244,14 +263,14 @@ pcr_fused_kernel(FusedArgs F) {
     // the CTAs that updated it, sweep 2 per band of t for the sweep-1 items that wrote it. A CTA
     // that is ahead no longer waits for the slowest one at two of the four grid barriers of an
     // iteration (the SMs' streaming rates differ by 10-15 %), it starts its next item instead.
-    const bool flags_on = F.t_ready != nullptr && F.nranks == 1 &&
+    const bool flags_on = F.t_ready != nullptr && nranks == 1 &&
                           F.T2.plan.nitems <= (int)gridDim.x;
     unsigned x_gen = 0;  // updates so far (identical in all CTAs)
 
     // lhs (own m-slice) = A W A' x; returns the total x'lhs to all threads. x_flagged: x was
     // written by the update stage and is guarded by x_ready (no grid barrier since);
     // extra_max: rides the reduction that ends the apply (the update's residual norm).
-    auto apply = [&](const double* x, double* lhs, bool x_flagged, double extra_max) -> double {
+    auto apply = [&](const double* x, double* lhs, bool x_flagged, double extra_max) __attribute__((always_inline)) -> double {
         BandArgs a1{x, F.Wc, nullptr, nullptr, F.t, kApplyPlain, kSlotNone};
         BandReady rx;
         if (flags_on && x_flagged) {
@@ -282,11 +301,20 @@ pcr_fused_kernel(FusedArgs F) {
         }
         const int nparts = F.T2.plan.nparts;
         double dot = 0.0;
-        if (F.nranks == 1 && F.T2.plan.nitems <= (int)gridDim.x) {
+        const bool fold_sharded = nranks > 1 && F.xfold && F.xll_off != 0 &&
+                                  F.T2.plan.nitems <= (int)gridDim.x;
+        if ((nranks == 1 || fold_sharded) && F.T2.plan.nitems <= (int)gridDim.x) {
             // The nparts items of a row block (all resident: one item per CTA)
             // meet at the block's counter when their partials are written; each
             // then combines its share of the block's rows, in part order. No
             // separate combine stage, one grid barrier less.
+            //
+            // Column shards (folded exchange): the share's rows are exchanged right there,
+            // while the items of other row blocks are still sweeping. Records are addressed by
+            // row, so the ranks need not cut their row blocks alike. One hop (2-3 ranks):
+            // every rank gets every rank's partial and sums them in rank order. Two hops (4 and
+            // more): row i belongs to rank i / ceil(m / nranks), which sums the ranks' partials
+            // in rank order and pushes the final value to everybody.
             ++s_applies;
             if ((int)blockIdx.x < F.T2.plan.nitems) {
                 const int item = blockIdx.x;
@@ -307,14 +335,65 @@ pcr_fused_kernel(FusedArgs F) {
                 const int rb = sb * F.T2.plan.SB, re = min(m, rb + F.T2.plan.SB);
                 const int share = (re - rb + nparts - 1) / nparts;
                 const int q0 = rb + part * share, q1 = min(re, q0 + share);
-                for (int i = q0 + tid; i < q1; i += nthr) {
-                    double acc = 0.0;
+                if (!fold_sharded) {
+                    for (int i = q0 + tid; i < q1; i += nthr) {
+                        double acc = 0.0;
 #pragma unroll 8
-                    for (int p = 0; p < nparts; p++) acc += __ldcg(F.T2.partials + (size_t)p * m + i);
-                    const double xv = __ldcg(x + i);
-                    const double yv = (F.Ws ? __dmul_rn(xv, F.Ws[i]) : 0.0) + acc;
-                    lhs[i] = yv;
-                    dot += __dmul_rn(xv, yv);
+                        for (int p = 0; p < nparts; p++) acc += __ldcg(F.T2.partials + (size_t)p * m + i);
+                        const double xv = __ldcg(x + i);
+                        const double yv = (F.Ws ? __dmul_rn(xv, F.Ws[i]) : 0.0) + acc;
+                        lhs[i] = yv;
+                        dot += __dmul_rn(xv, yv);
+                    }
+                } else {
+                    const unsigned gen = F.xgen_base + (unsigned)s_applies;
+                    const size_t par = (size_t)(gen & 1u) * (size_t)nranks * F.xmpad;
+                    const size_t fin_off = F.xll_off + 2 * (size_t)nranks * F.xmpad * 16 +
+                                           (size_t)(gen & 1u) * F.xmpad * 16;
+                    const int rows_per_rank = (m + nranks - 1) / nranks;
+                    char* const own = reinterpret_cast<char*>(F.peers[F.rank]);
+                    const ulonglong2* own_rec = reinterpret_cast<const ulonglong2*>(own + F.xll_off) + par;
+                    const ulonglong2* fin = reinterpret_cast<const ulonglong2*>(own + fin_off);
+                    // pass 1: this rank's partial of every row, pushed
+                    for (int i = q0 + tid; i < q1; i += nthr) {
+                        double acc = 0.0;
+#pragma unroll 8
+                        for (int p = 0; p < nparts; p++) acc += __ldcg(F.T2.partials + (size_t)p * m + i);
+                        const double mine = (F.Ws ? __dmul_rn(__ldcg(x + i), F.Ws[i]) : 0.0) + acc;
+                        const int r0x = F.xtwo_phase ? i / rows_per_rank : 0;
+                        const int r1x = F.xtwo_phase ? r0x + 1 : nranks;
+                        for (int r = r0x; r < r1x; r++)
+                            xll_store(reinterpret_cast<ulonglong2*>(
+                                          reinterpret_cast<char*>(F.peers[r]) + F.xll_off) +
+                                          par + (size_t)F.rank * F.xmpad + i, gen, mine);
+                    }
+                    // pass 2: sum in rank order - every row (one hop) or the rows this rank owns,
+                    // whose finals go to everybody (two hops)
+                    for (int i = q0 + tid; i < q1; i += nthr) {
+                        if (F.xtwo_phase && i / rows_per_rank != F.rank) continue;
+                        double tot = 0.0;
+                        for (int r = 0; r < nranks; r++) {
+                            double part_r = 0.0;
+                            xchg_wait(own_rec + (size_t)r * F.xmpad + i, gen, &part_r, F.abort_word);
+                            tot += part_r;
+                        }
+                        if (F.xtwo_phase) {
+                            for (int r = 0; r < nranks; r++)
+                                xll_store(reinterpret_cast<ulonglong2*>(
+                                              reinterpret_cast<char*>(F.peers[r]) + fin_off) + i, gen, tot);
+                        } else {
+                            lhs[i] = tot;
+                            dot += __dmul_rn(__ldcg(x + i), tot);
+                        }
+                    }
+                    // pass 3 (two hops): the finals
+                    if (F.xtwo_phase)
+                        for (int i = q0 + tid; i < q1; i += nthr) {
+                            double yv = 0.0;
+                            xchg_wait(fin + i, gen, &yv, F.abort_word);
+                            lhs[i] = yv;
+                            dot += __dmul_rn(__ldcg(x + i), yv);
+                        }
                 }
             }
         } else {
@@ -323,7 +402,9 @@ pcr_fused_kernel(FusedArgs F) {
                 band_sweep_item<NW, D, DBG>(F.T2, a2, kBandPartial, item, smem_raw);
             sync_plain();
         }
-        if (F.nranks == 1 && F.T2.plan.nitems > (int)gridDim.x) {
+        if (fold_sharded) {
+            // (rows exchanged above)
+        } else if (nranks == 1 && F.T2.plan.nitems > (int)gridDim.x) {
             for (int i = i0 + tid; i < i1; i += nthr) {
                 double acc = 0.0;
 #pragma unroll 8
@@ -333,7 +414,7 @@ pcr_fused_kernel(FusedArgs F) {
                 lhs[i] = yv;
                 dot += __dmul_rn(xv, yv);
             }
-        } else if (F.nranks > 1 && F.xll_off != 0 && F.xtwo_phase) {
+        } else if (nranks > 1 && F.xll_off != 0 && F.xtwo_phase) {
             // Column shards, two-phase push exchange (4 and more ranks): the slice of CTA c is
             // cut into one piece per rank. Every rank pushes its partial products of piece r
             // to rank r only; rank r sums the ranks' records of its piece in rank order and
@@ -343,10 +424,10 @@ pcr_fused_kernel(FusedArgs F) {
             // stay bit-identical. Records validate themselves: no flags, fences or barriers;
             // the three steps are chained per thread.
             const unsigned gen = F.xgen_base + (unsigned)s_applies;
-            const size_t par = (size_t)(gen & 1u) * (size_t)F.nranks * F.xmpad;
-            const size_t fin_off = F.xll_off + 2 * (size_t)F.nranks * F.xmpad * 16 +
+            const size_t par = (size_t)(gen & 1u) * (size_t)nranks * F.xmpad;
+            const size_t fin_off = F.xll_off + 2 * (size_t)nranks * F.xmpad * 16 +
                                    (size_t)(gen & 1u) * F.xmpad * 16;
-            const int per = (i1 - i0 + F.nranks - 1) / F.nranks;
+            const int per = (i1 - i0 + nranks - 1) / nranks;
             auto wait_rec = [&](const ulonglong2* p, double* val) {
                 long long spins = 0;
                 while (!xll_load(p, gen, val)) {
@@ -374,12 +455,12 @@ pcr_fused_kernel(FusedArgs F) {
                                                 reinterpret_cast<const char*>(F.peers[F.rank]) +
                                                 F.xll_off) + par + i;
                     double tot = 0.0;
-                    for (int r = 0; r < F.nranks; r++) {
+                    for (int r = 0; r < nranks; r++) {
                         double part;
                         wait_rec(rec + (size_t)r * F.xmpad, &part);
                         tot += part;
                     }
-                    for (int r = 0; r < F.nranks; r++)
+                    for (int r = 0; r < nranks; r++)
                         xll_store(reinterpret_cast<ulonglong2*>(
                                       reinterpret_cast<char*>(F.peers[r]) + fin_off) + i, gen, tot);
                 }
@@ -392,7 +473,7 @@ pcr_fused_kernel(FusedArgs F) {
                 lhs[i] = yv;
                 dot += __dmul_rn(x[i], yv);
             }
-        } else if (F.nranks > 1 && F.xll_off != 0) {
+        } else if (nranks > 1 && F.xll_off != 0) {
             // Column shards, push exchange: every rank writes its partial product of the slice
             // straight into every rank's record buffer (posted NVLink stores), then sums the
             // ranks' records of the slice from its OWN memory in rank order - bit-identical on
@@ -400,13 +481,13 @@ pcr_fused_kernel(FusedArgs F) {
             // fence.sys and no load round trip over NVLink; buffers alternate by generation
             // parity (a rank can be at most one exchange ahead of a peer).
             const unsigned gen = F.xgen_base + (unsigned)s_applies;
-            const size_t par = (size_t)(gen & 1u) * (size_t)F.nranks * F.xmpad;
+            const size_t par = (size_t)(gen & 1u) * (size_t)nranks * F.xmpad;
             for (int i = i0 + tid; i < i1; i += nthr) {
                 double acc = 0.0;
 #pragma unroll 8
                 for (int p = 0; p < nparts; p++) acc += __ldcg(F.T2.partials + (size_t)p * m + i);
                 const double mine = (F.Ws ? __dmul_rn(x[i], F.Ws[i]) : 0.0) + acc;
-                for (int r = 0; r < F.nranks; r++) {
+                for (int r = 0; r < nranks; r++) {
                     ulonglong2* dst = reinterpret_cast<ulonglong2*>(
                                           reinterpret_cast<char*>(F.peers[r]) + F.xll_off) +
                                       par + (size_t)F.rank * F.xmpad + i;
@@ -417,13 +498,13 @@ pcr_fused_kernel(FusedArgs F) {
                                         reinterpret_cast<const char*>(F.peers[F.rank]) + F.xll_off) + par;
             for (int i = i0 + tid; i < i1; i += nthr) {
                 double yv = 0.0;
-                for (int rb = 0; rb < F.nranks; rb += 8) {
+                for (int rb = 0; rb < nranks; rb += 8) {
                     double part[8];
                     bool ok[8];
 #pragma unroll
                     for (int u = 0; u < 8; u++) {
                         part[u] = 0.0;
-                        ok[u] = rb + u >= F.nranks ||
+                        ok[u] = rb + u >= nranks ||
                                 xll_load(rec + (size_t)(rb + u) * F.xmpad + i, gen, &part[u]);
                     }
 #pragma unroll
@@ -442,12 +523,12 @@ pcr_fused_kernel(FusedArgs F) {
                     }
 #pragma unroll
                     for (int u = 0; u < 8; u++)
-                        if (rb + u < F.nranks) yv += part[u];
+                        if (rb + u < nranks) yv += part[u];
                 }
                 lhs[i] = yv;
                 dot += __dmul_rn(x[i], yv);
             }
-        } else if (F.nranks > 1) {
+        } else if (nranks > 1) {
             // Column shards, pull exchange (IPXGPU_XCHG=pull): this rank's partial product of the slice goes to its
             // exchange buffer; the same CTA of every rank then sums the ranks'
             // partials of the slice in rank order (bit-identical on all ranks)
@@ -466,7 +547,7 @@ pcr_fused_kernel(FusedArgs F) {
             const size_t flag_off = 2 * F.xmpad;  // in doubles
             if (tid == 0) __threadfence_system();
             __syncthreads();
-            if (tid < F.nranks) {
+            if (tid < nranks) {
                 // signal rank `tid` that slice blockIdx.x of this rank is ready ...
                 unsigned* remote = reinterpret_cast<unsigned*>(F.peers[tid] + flag_off) +
                                    (size_t)F.rank * gridDim.x + blockIdx.x;
@@ -493,19 +574,19 @@ pcr_fused_kernel(FusedArgs F) {
                 // All peers' loads go out before the first sum waits (one NVLink round
                 // trip per group of 8 ranks instead of one per rank); summed in rank order.
                 double yv = 0.0;
-                for (int rb = 0; rb < F.nranks; rb += 8) {
+                for (int rb = 0; rb < nranks; rb += 8) {
                     double part[8];
 #pragma unroll
                     for (int u = 0; u < 8; u++) {
                         part[u] = 0.0;
-                        if (rb + u < F.nranks)
+                        if (rb + u < nranks)
                             asm volatile("ld.relaxed.sys.global.f64 %0, [%1];"
                                          : "=d"(part[u])
                                          : "l"(F.peers[rb + u] + off + i));
                     }
 #pragma unroll
                     for (int u = 0; u < 8; u++)
-                        if (rb + u < F.nranks) yv += part[u];
+                        if (rb + u < nranks) yv += part[u];
                 }
                 lhs[i] = yv;
                 dot += __dmul_rn(x[i], yv);
