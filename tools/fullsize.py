@@ -236,6 +236,17 @@ def run_basis_checks(name, lp, reflib, gpulib, log=print, kkt_maxiter=200, volum
         out[f"kkt_solve_{key}"] = {k: info[k] for k in ("err", "kktiter2", "time_cr2", "time_cr2_NNt",
                                                         "time_cr2_B", "time_cr2_Bt")}
         sol[key] = (x, y, info)
+    # The same solve cut off after a few CR iterations, while the two arms' Krylov iterates
+    # have not parted ways yet: what the device does around the CR loop (right-hand side
+    # sweeps, the Basis::SolveDense steps, the recovery sweeps) against the reference's.
+    short = {}
+    for key, mdl in (("ref", ref), ("gpu", gpu)):
+        mdl.kktbasis_maxiter(5)
+        short[key] = mdl.kktbasis_solve(a, b, 1e-6)
+        mdl.kktbasis_maxiter(kkt_maxiter)
+    out["kkt5_x_rel_err"] = rel_err(short["gpu"][0], short["ref"][0])
+    out["kkt5_y_rel_err"] = rel_err(short["gpu"][1], short["ref"][1])
+    out["kkt5_iter"] = (int(short["ref"][2]["kktiter2"]), int(short["gpu"][2]["kktiter2"]))
     (x0, y0, i0), (x1, y1, i1) = sol["ref"], sol["gpu"]
     assert i0["err"] == i1["err"], (i0, i1)
     if i0["err"] == 0:
