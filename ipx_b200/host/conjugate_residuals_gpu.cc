@@ -66,6 +66,7 @@ void ConjugateResiduals::Solve(LinearOperator& C, const Vector& rhs, double tol,
 
     if (OperatorRecord* dev = DeviceOperator(C)) {
         ipxgpu_cr_result res{};
+        ipxb200::EnsurePrimed(*dev, &C);
         if (m > 0) {
             const int op = dev->kind == OperatorKind::kSplit ? 1 : 0;
             Check(ipxgpu_cr_solve(dev->ref.ctx, op, &rhs[0], tol, resscale, maxiter, &lhs[0], &res,
@@ -102,6 +103,8 @@ void ConjugateResiduals::Solve(LinearOperator& C, LinearOperator& P, const Vecto
                              ipxb200::StillCurrent(*devP) && devP->ref.ctx == devC->ref.ctx;
     if (device_loop) {
         ipxgpu_cr_result res{};
+        ipxb200::EnsurePrimed(*devC, &C);
+        ipxb200::EnsurePrimed(*devP, &P);
         if (m > 0) {
             Check(ipxgpu_pcr_solve(devC->ref.ctx, &rhs[0], tol, resscale, maxiter, &lhs[0], &res,
                                    InterruptThunk, const_cast<Control*>(&control_), nullptr, 0));

@@ -57,6 +57,17 @@ void DiagonalPrecond::Factorize(const double* W, bool precond_dense_cols, Info* 
     rec.ref = ref;
     rec.model = &model_;
     rec.time = &time_;
+    // Puts E (and the dense-column factor) of THIS object back on the device: after the context
+    // was rebuilt, or after another preconditioner on the same model was factorized.
+    rec.reprime = [this] {
+        OperatorRecord& r = ipxb200::RecordOf(this);
+        r.ref = ipxb200::ContextFor(model_);
+        if (model_.rows() > 0) Check(ipxgpu_diag_set(r.ref.ctx, &diagonal_[0]));
+        if (Atdense_.rows() > 0) LoadDenseColumnPart(r.ref.ctx, Atdense_, chol_factor_);
+        else Check(ipxgpu_smw_clear(r.ref.ctx));
+        ipxb200::ClaimState(r.ref.ctx, ipxb200::StateSlot::kDiagonal, this);
+    };
+    ipxb200::ClaimState(ref.ctx, ipxb200::StateSlot::kDiagonal, this);
 
     if (!smw) {
         // diag(AI*W*AI') over all columns, on the device (possibly already there).
@@ -118,12 +129,9 @@ void DiagonalPrecond::_Apply(const Vector& rhs, Vector& lhs, double* rhs_dot_lhs
     assert((Int)rhs.size() == m);
 
     OperatorRecord& rec = ipxb200::RecordOf(this);
-    if (!ipxb200::StillCurrent(rec)) {  // context was rebuilt: reinstall E (and the factor)
-        rec.ref = ipxb200::ContextFor(model_);
-        if (m > 0) Check(ipxgpu_diag_set(rec.ref.ctx, &diagonal_[0]));
-        if (Atdense_.rows() > 0) LoadDenseColumnPart(rec.ref.ctx, Atdense_, chol_factor_);
-        else Check(ipxgpu_smw_clear(rec.ref.ctx));
-    }
+    if (!ipxb200::StillCurrent(rec) ||
+        !ipxb200::OwnsState(rec.ref.ctx, ipxb200::StateSlot::kDiagonal, this))
+        rec.reprime();
     double dot = 0.0;
     if (m > 0) Check(ipxgpu_diag_apply(rec.ref.ctx, &rhs[0], &lhs[0], &dot));
     if (rhs_dot_lhs) *rhs_dot_lhs = dot;

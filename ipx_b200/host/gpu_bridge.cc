@@ -1,5 +1,6 @@
 #include "gpu_bridge.h"
 
+#include <array>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -28,6 +29,7 @@ struct Tables {
     std::unordered_map<const ipx::Model*, ModelEntry> models;
     std::unordered_map<const ipx::Model*, ModelEntry> groups;  // multi-GPU groups (IPXGPU_NGPUS)
     std::unordered_map<const ipx::LinearOperator*, OperatorRecord> operators;
+    std::unordered_map<const ipxgpu_ctx*, std::array<const void*, (size_t)StateSlot::kCount>> owners;
     unsigned long long generation = 0, clock = 0;
     ~Tables() {
         for (auto& kv : models)
@@ -109,7 +111,10 @@ ContextRef ContextFor(const ipx::Model& model) {
             e.last_use = ++t.clock;
             return ContextRef{e.ctx, e.generation};
         }
-        if (e.ctx) ipxgpu_destroy(e.ctx);
+        if (e.ctx) {
+            t.owners.erase(e.ctx);
+            ipxgpu_destroy(e.ctx);
+        }
         t.models.erase(it);
     }
     // Model has no destructor hook: evict the least recently used context
@@ -118,7 +123,10 @@ ContextRef ContextFor(const ipx::Model& model) {
         auto victim = t.models.begin();
         for (auto jt = t.models.begin(); jt != t.models.end(); ++jt)
             if (jt->second.last_use < victim->second.last_use) victim = jt;
-        if (victim->second.ctx) ipxgpu_destroy(victim->second.ctx);
+        if (victim->second.ctx) {
+            t.owners.erase(victim->second.ctx);
+            ipxgpu_destroy(victim->second.ctx);
+        }
         t.models.erase(victim);
     }
     ipxgpu_options opt;
@@ -224,6 +232,36 @@ bool StillCurrent(const OperatorRecord& rec) {
     if (!rec.model || !rec.ref.ctx) return false;
     const ContextRef cur = CurrentContext(*rec.model);
     return cur.ctx == rec.ref.ctx && cur.generation == rec.ref.generation;
+}
+
+void ClaimState(ipxgpu_ctx* ctx, StateSlot slot, const void* owner) {
+    Tables& t = tables();
+    std::lock_guard<std::mutex> lock(t.mutex);
+    auto it = t.owners.find(ctx);
+    if (it == t.owners.end()) it = t.owners.emplace(ctx, decltype(t.owners)::mapped_type{}).first;
+    it->second[(size_t)slot] = owner;
+}
+
+bool OwnsState(ipxgpu_ctx* ctx, StateSlot slot, const void* owner) {
+    Tables& t = tables();
+    std::lock_guard<std::mutex> lock(t.mutex);
+    auto it = t.owners.find(ctx);
+    return it != t.owners.end() && it->second[(size_t)slot] == owner;
+}
+
+void EnsurePrimed(OperatorRecord& rec, const ipx::LinearOperator* op) {
+    StateSlot slot;
+    switch (rec.kind) {
+        case OperatorKind::kNormal: slot = StateSlot::kWeights; break;
+        case OperatorKind::kDiagonal: slot = StateSlot::kDiagonal; break;
+        case OperatorKind::kSplit: slot = StateSlot::kSplit; break;
+        default: return;
+    }
+    if (OwnsState(rec.ref.ctx, slot, op)) return;
+    if (!rec.reprime)
+        throw std::logic_error("another operator instance on this model has replaced the device "
+                               "state of this one; prepare it again");
+    rec.reprime();
 }
 
 void SetResidentHint(ipxgpu_ctx* ctx, const double* W) {

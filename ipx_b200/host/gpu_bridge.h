@@ -12,6 +12,8 @@
 #ifndef IPXB200_GPU_BRIDGE_H_
 #define IPXB200_GPU_BRIDGE_H_
 
+#include <functional>
+
 #include "ipxgpu.h"
 #include "linear_operator.h"
 #include "model.h"
@@ -56,7 +58,21 @@ struct OperatorRecord {
     double* time_B = nullptr;   // SplittedNormalMatrix accumulators
     double* time_Bt = nullptr;
     double* time_NNt = nullptr;
+    // Puts this operator's state back on the device when another instance on the same model
+    // has primed the context since (empty: the operator cannot; its user must prepare again).
+    std::function<void()> reprime;
 };
+
+// A context holds ONE set of weights, ONE diagonal, ONE set of factors ... while the reference's
+// classes each own theirs. Whoever primes a part of the context claims it; before an object
+// uses the device state it checks that the claim is still its own and re-primes (or refuses)
+// otherwise, so two live instances on one Model cannot silently use each other's state.
+enum class StateSlot : int { kWeights = 0, kDiagonal, kSplit, kKktDiag, kCount };
+void ClaimState(ipxgpu_ctx* ctx, StateSlot slot, const void* owner);
+bool OwnsState(ipxgpu_ctx* ctx, StateSlot slot, const void* owner);
+// Re-primes the operator behind `rec` if its claim was taken; throws std::logic_error when
+// the operator cannot re-prime itself.
+void EnsurePrimed(OperatorRecord& rec, const ipx::LinearOperator* op);
 
 // Record of an operator instance (keyed by its LinearOperator base address).
 OperatorRecord& RecordOf(const ipx::LinearOperator* op);

@@ -130,6 +130,8 @@ void KKTSolverBasis::_Solve(const Vector& a, const Vector& b, double tol, Vector
     const ipxb200::ContextRef ref = ipxb200::CurrentContext(model_);
     if (!ref.ctx) throw std::logic_error("KKTSolverBasis: device context lost; call Factorize again");
     ipxgpu_cr_result res{};
+    if (ipxb200::OperatorRecord* op = ipxb200::FindRecord(&splitted_normal_matrix_))
+        ipxb200::EnsurePrimed(*op, &splitted_normal_matrix_);  // throws if another basis took over
     const int rc = ipxgpu_kktbasis_solve(ref.ctx, &a[0], &b[0], tol, maxiter_, &x[0], &y[0], &res,
                                          InterruptThunk, const_cast<Control*>(&control_));
     if (rc == IPXGPU_ERR_STATE)

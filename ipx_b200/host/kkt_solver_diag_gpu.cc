@@ -71,6 +71,7 @@ void KKTSolverDiag::_Factorize(Iterate* pt, Info* info) {
                                        pt ? &pt->zu()[0] : nullptr, pt ? pt->mu() : 0.0, &W_[0],
                                        &resscale_[0]));
         lap("ipxgpu_kktdiag_factorize (group)");
+        ipxb200::ClaimState(ref.ctx, ipxb200::StateSlot::kKktDiag, this);
         factorized_ = true;
         return;
     }
@@ -88,6 +89,7 @@ void KKTSolverDiag::_Factorize(Iterate* pt, Info* info) {
         // Weights and diagonal are already resident: the member operators only
         // register themselves (and fetch the diagonal).
         ipxb200::SetResidentHint(ref.ctx, &W_[0]);
+        ipxb200::ClaimState(ref.ctx, ipxb200::StateSlot::kKktDiag, this);
         lap("ipxgpu_kktdiag_factorize");
     }
     normal_matrix_.Prepare(&W_[0]);
@@ -112,6 +114,16 @@ void KKTSolverDiag::_Solve(const Vector& a, const Vector& b, double tol, Vector&
         return;
     }
     if (!ref.ctx) throw std::logic_error("KKTSolverDiag: no device context; call Factorize first");
+    if (!ipxb200::OwnsState(ref.ctx, ipxb200::StateSlot::kKktDiag, this))
+        throw std::logic_error("KKTSolverDiag: another solver was factorized on this model since; "
+                               "call Factorize again");
+    // weights and preconditioner on the device belong to the member operators
+    if (!UseGroup(control_, model_)) {
+        if (ipxb200::OperatorRecord* c = ipxb200::FindRecord(&normal_matrix_))
+            ipxb200::EnsurePrimed(*c, &normal_matrix_);
+        if (ipxb200::OperatorRecord* p = ipxb200::FindRecord(&precond_))
+            ipxb200::EnsurePrimed(*p, &precond_);
+    }
 
     ipxgpu_cr_result res{};
     int rc = ipxgpu_kktdiag_solve(ref.ctx, &a[0], &b[0], tol, maxiter_, &x[0], &y[0], &res,

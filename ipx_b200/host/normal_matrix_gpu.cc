@@ -34,6 +34,8 @@ void NormalMatrix::Prepare(const double* W) {
     rec.ref = ref;
     rec.model = &model_;
     rec.time = &time_;
+    rec.reprime = [this] { Prepare(W_); };
+    ipxb200::ClaimState(ref.ctx, ipxb200::StateSlot::kWeights, this);
     prepared_ = true;
 }
 
@@ -49,7 +51,10 @@ void NormalMatrix::_Apply(const Vector& rhs, Vector& lhs, double* rhs_dot_lhs) {
     assert((Int)lhs.size() == m);
     assert((Int)rhs.size() == m);
     OperatorRecord& rec = ipxb200::RecordOf(this);
-    if (!ipxb200::StillCurrent(rec)) Prepare(W_);  // context was rebuilt
+    // context rebuilt, or its weights replaced by another instance on this model: prime again
+    if (!ipxb200::StillCurrent(rec) ||
+        !ipxb200::OwnsState(rec.ref.ctx, ipxb200::StateSlot::kWeights, this))
+        Prepare(W_);
     if (m > 0)
         Check(ipxgpu_normal_apply(rec.ref.ctx, &rhs[0], &lhs[0], rhs_dot_lhs));
     else if (rhs_dot_lhs)

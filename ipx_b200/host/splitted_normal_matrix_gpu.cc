@@ -83,6 +83,8 @@ void SplittedNormalMatrix::Prepare(const Basis& basis, const double* colscale) {
     rec.time_B = &time_B_;
     rec.time_Bt = &time_Bt_;
     rec.time_NNt = &time_NNt_;
+    rec.reprime = nullptr;  // needs the basis: Prepare again
+    ipxb200::ClaimState(ref.ctx, ipxb200::StateSlot::kSplit, this);
     prepared_ = true;
 }
 
@@ -108,6 +110,7 @@ void SplittedNormalMatrix::_Apply(const Vector& rhs, Vector& lhs, double* rhs_do
     OperatorRecord& rec = ipxb200::RecordOf(this);
     if (!ipxb200::StillCurrent(rec))
         throw std::logic_error("SplittedNormalMatrix: device context was rebuilt; call Prepare");
+    ipxb200::EnsurePrimed(rec, this);
     if (rhs.size() > 0)
         Check(ipxgpu_split_apply(rec.ref.ctx, &rhs[0], &lhs[0], rhs_dot_lhs));
     else if (rhs_dot_lhs)

@@ -130,6 +130,38 @@ def test_kkt_solver_diag(pair):
     assert rel_err(out[1][1], out[0][1]) <= 1e-5
 
 
+def test_two_operator_instances_on_one_model(pair):
+    """The reference's classes each own their weights; the device context of a model holds one
+    set. The harness' stand-alone NormalMatrix / DiagonalPrecond and the members of its
+    KKTSolverDiag are two instances each on the same Model: whoever is used after the other
+    one primed the context must get ITS state back (gpu_bridge.h: ClaimState / EnsurePrimed)."""
+    lp, ref, gpu = pair
+    m, n = ref.m, ref.n
+    _, _, lb, ub = ref.model_vectors()
+    it = _iterate(m, n, lb, ub, 21)
+    rng = np.random.default_rng(22)
+    W1 = lpgen.weights(n + m, "mid", 23)
+    x = rng.standard_normal(m)
+    a, b = rng.standard_normal(n + m), rng.standard_normal(m)
+    out = []
+    for mdl in (ref, gpu):
+        mdl.normal_prepare(W1)                   # stand-alone instances: weights W1
+        assert mdl.diag_factorize(W1) == 0
+        mdl.iterate_set(*it)
+        assert mdl.kktdiag_factorize(True) == 0  # the solver's members: the iterate's weights
+        y_a, _ = mdl.normal_apply(x)             # must still be A*W1*A'
+        l_a, _ = mdl.diag_apply(x)
+        sol = mdl.kktdiag_solve(a, b, 1e-8)      # and the solver must get its own state back
+        y_b, _ = mdl.normal_apply(x)
+        out.append((y_a, l_a, sol, y_b))
+    (ya0, la0, s0, yb0), (ya1, la1, s1, yb1) = out
+    assert rel_err(ya1, ya0) <= 1e-12 and rel_err(yb1, yb0) <= 1e-12
+    assert rel_err(la1, la0) <= 1e-12
+    assert s0[2]["err"] == s1[2]["err"] == 0
+    assert abs(s0[2]["kktiter1"] - s1[2]["kktiter1"]) <= 1
+    assert rel_err(s1[1], s0[1]) <= 1e-6 and rel_err(s1[0], s0[0]) <= 1e-6
+
+
 def test_splitted_normal_matrix_and_basis_cr(pair):
     lp, ref, gpu = pair
     m, n = ref.m, ref.n

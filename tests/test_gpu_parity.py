@@ -128,14 +128,23 @@ def test_pcr_matches_oracle(problem, oracle, tol):
     y0, info0 = oracle.pcr_solve(oracle.normal_operator(m, n, A, W), m, diag, rhs, tol, resscale,
                                  -1, hist_cap=4096)
     assert info["errflag"] == info0["errflag"]
-    # Residual histories: the first passes agree to rounding; later ones only
-    # loosely, because CR amplifies summation-order differences on
-    # ill-conditioned systems (the ragged case has a dense column), which can
-    # also shift the pass at which the tolerance is crossed.
-    k = min(len(info["hist"]), len(info0["hist"]), 5)
-    assert np.allclose(info["hist"][:k], info0["hist"][:k], rtol=1e-9, atol=0.0)
-    assert abs(info["iter"] - info0["iter"]) <= max(1, info0["iter"] // 10)
-    assert rel_err(y, y0) <= max(1e-4, 10 * tol)
+    # CR amplifies rounding on ill-conditioned systems (the ragged case has a dense column), so
+    # the bar is the oracle's own sensitivity: the same solve with a right-hand side that differs
+    # by one ulp per entry. Where the oracle agrees with itself to rounding, so must the device
+    # (1e-9 on the residual norms and on the iterate); where it does not, the device may be a
+    # few times as far from the oracle as the oracle is from itself. One pass more or fewer is
+    # allowed where a residual norm lies within rounding of the tolerance.
+    ulp = np.spacing(np.abs(rhs)) * rng.choice([-1.0, 1.0], m)
+    y1, info1 = oracle.pcr_solve(oracle.normal_operator(m, n, A, W), m, diag, rhs + ulp, tol,
+                                 resscale, -1, hist_cap=4096)
+    h, h0, h1 = info["hist"], info0["hist"], info1["hist"]
+    k = min(len(h), len(h0), len(h1))
+    self_dev = np.maximum.accumulate(np.abs(h1[:k] - h0[:k]) / h0[:k])
+    assert np.all(np.abs(h[:k] - h0[:k]) <= np.maximum(1e-9, 50 * self_dev) * h0[:k])
+    assert abs(info["iter"] - info0["iter"]) <= 1
+    if info["iter"] == info0["iter"]:
+        self_err = rel_err(y1, y0) if info1["iter"] == info0["iter"] else 1.0
+        assert rel_err(y, y0) <= max(1e-9, 50 * self_err)
     # the returned iterate solves the system to the requested accuracy
     Cy, _ = oracle.normal_apply(m, n, A, W, y)
     if info["errflag"] == 0:
