@@ -300,6 +300,41 @@ int ipxgpu_kktbasis_solve(ipxgpu_ctx* ctx, const double* a, const double* b,
                           ipxgpu_cr_result* result,
                           ipxgpu_interrupt_fn interrupt, void* user);
 
+/* ---- Maxvolume column sweeps (reference src/maxvolume.cc:170-320) ---- */
+
+/* What FindLargest (src/maxvolume.cc:170-200) returns over the resident
+ * weights: the column of the largest |weight| (the first one among equals)
+ * and of the second largest, 0 with weight 0 where there is none. */
+typedef struct ipxgpu_maxvol_top {
+    int64_t jmax, jmax2;
+    double wmax, wmax2; /* |colweights[jmax]|, |colweights[jmax2]| */
+} ipxgpu_maxvol_top;
+
+/* Opening of a Maxvolume::Driver call (src/maxvolume.cc:220-231):
+ * colweights[j] = (AI[:,j]'work) * colscale[j] where colscale[j] != 0, else 0,
+ * over all n+m columns of the resident AI; then FindLargest. colscale (n+m host
+ * doubles) is uploaded and stays resident with the weights until
+ * ipxgpu_maxvol_release; NULL keeps the resident factors of the previous call
+ * (the next slice of the same run). work: m host doubles. Unsharded contexts. */
+int ipxgpu_maxvol_weights(ipxgpu_ctx* ctx, const double* colscale,
+                          const double* work, ipxgpu_maxvol_top* top);
+/* A column the heuristic gives up on (:262-265): colweights[j] = colscale[j] =
+ * 0 (j = -1: no column). top != NULL: FindLargest over the resident weights. */
+int ipxgpu_maxvol_skip(ipxgpu_ctx* ctx, int64_t j, ipxgpu_maxvol_top* top);
+/* One basis update (:280-309), after jb left and jn entered the basis:
+ * colscale[jb] = colscale_jb, colscale[jn] = 0; the tableau row of jb over the
+ * nonbasic columns, row[j] = AI[:,j]'btran (Basis::TableauRow's dense branch,
+ * src/basis.cc:266-279), folded into colweights[j] += alpha * row[j] *
+ * colscale[j]; colweights[jb] = colweight_jb, colweights[jn] = 0; FindLargest.
+ * btran: m host doubles (row of inverse(B) of the leaving variable). */
+int ipxgpu_maxvol_update(ipxgpu_ctx* ctx, const double* btran, double alpha,
+                         int64_t jb, double colscale_jb, double colweight_jb,
+                         int64_t jn, ipxgpu_maxvol_top* top);
+/* Copies the resident factors / weights to the host (either may be NULL). */
+int ipxgpu_maxvol_get(ipxgpu_ctx* ctx, double* colscale, double* colweights);
+/* Frees the resident factors and weights (end of RunHeuristic). */
+int ipxgpu_maxvol_release(ipxgpu_ctx* ctx);
+
 /* ---- measurement helpers ---- */
 
 /* Runs `reps` device-resident normal-matrix applies on resident vectors and

@@ -25,7 +25,7 @@ LIBIPX_GPU = os.path.join(OUT, "libipx_gpu.so")
 
 # Reference TUs replaced by ipx_b200/host/*_gpu.cc.
 REPLACED = ["normal_matrix", "diagonal_precond", "conjugate_residuals", "splitted_normal_matrix",
-            "kkt_solver_diag", "kkt_solver_basis"]
+            "kkt_solver_diag", "kkt_solver_basis", "maxvolume"]
 ABSENT = ["basiclu_wrapper", "basiclu_kernel"]  # need the un-vendored BASICLU
 SHIMS = ["lu_provider", "sparse_lu", "lapack_min"]
 

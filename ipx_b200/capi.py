@@ -23,6 +23,13 @@ class Options(C.Structure):
                 ("col_begin", i64), ("col_end", i64), ("panel_cols", i64), ("stream", C.c_void_p)]
 
 
+class MaxvolTop(C.Structure):
+    _fields_ = [("jmax", i64), ("jmax2", i64), ("wmax", C.c_double), ("wmax2", C.c_double)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 class CrResult(C.Structure):
     _fields_ = [("errflag", i64), ("iter", i64), ("time", C.c_double), ("time_op", C.c_double),
                 ("time_pre", C.c_double), ("time_B", C.c_double), ("time_Bt", C.c_double),
@@ -41,7 +48,9 @@ EXPORTS = ("ipxgpu_default_options ipxgpu_last_error ipxgpu_device_count ipxgpu_
            "ipxgpu_diag_factorize_masked ipxgpu_smw_load ipxgpu_smw_clear ipxgpu_create_group "
            "ipxgpu_diag_apply ipxgpu_pcr_solve ipxgpu_pcr_solve_dev ipxgpu_cr_solve ipxgpu_kktdiag_factorize "
            "ipxgpu_kktdiag_solve ipxgpu_lu_load ipxgpu_tri_solve ipxgpu_split_prepare "
-           "ipxgpu_split_apply ipxgpu_kktbasis_prepare ipxgpu_basis_solve ipxgpu_kktbasis_solve ipxgpu_time_normal_apply ipxgpu_launch_count ipxgpu_band_selftest ipxgpu_peer_export ipxgpu_peer_import").split()
+           "ipxgpu_split_apply ipxgpu_kktbasis_prepare ipxgpu_basis_solve ipxgpu_kktbasis_solve ipxgpu_time_normal_apply ipxgpu_launch_count ipxgpu_band_selftest ipxgpu_peer_export ipxgpu_peer_import "
+           "ipxgpu_maxvol_weights ipxgpu_maxvol_skip ipxgpu_maxvol_update ipxgpu_maxvol_get "
+           "ipxgpu_maxvol_release").split()
 
 _lib = None
 
@@ -324,6 +333,32 @@ class Context:
                                               _d(x), _d(y), C.byref(res),
                                               C.cast(None, INTERRUPT_FN), None))
         return x, y, res.asdict()
+
+    # ---- Maxvolume column sweeps ----
+    def maxvol_weights(self, colscale, work):
+        cs, w, top = _f64(colscale), _f64(work), MaxvolTop()
+        _check(self.lib.ipxgpu_maxvol_weights(self.h, _d(cs), _d(w), C.byref(top)))
+        return top.asdict()
+
+    def maxvol_skip(self, j, search=True):
+        top = MaxvolTop()
+        _check(self.lib.ipxgpu_maxvol_skip(self.h, i64(j), C.byref(top) if search else None))
+        return top.asdict() if search else None
+
+    def maxvol_update(self, btran, alpha, jb, colscale_jb, colweight_jb, jn):
+        b, top = _f64(btran), MaxvolTop()
+        _check(self.lib.ipxgpu_maxvol_update(self.h, _d(b), C.c_double(alpha), i64(jb),
+                                             C.c_double(colscale_jb), C.c_double(colweight_jb),
+                                             i64(jn), C.byref(top)))
+        return top.asdict()
+
+    def maxvol_get(self):
+        cs, cw = np.empty(self.n + self.m), np.empty(self.n + self.m)
+        _check(self.lib.ipxgpu_maxvol_get(self.h, _d(cs), _d(cw)))
+        return cs, cw
+
+    def maxvol_release(self):
+        _check(self.lib.ipxgpu_maxvol_release(self.h))
 
     # ---- measurement ----
     def time_normal_apply(self, reps, flush_l2=True):

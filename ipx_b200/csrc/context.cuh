@@ -108,6 +108,7 @@ inline int upload(T** dst, const std::vector<T>& src, cudaStream_t s) {
 
 struct SplitOperator;  // split.cuh
 struct BandDev;        // band_sweep.cuh
+struct Top2;           // maxvol.cuh
 
 }  // namespace ipxgpu
 
@@ -170,6 +171,15 @@ struct ipxgpu_ctx {
     unsigned tri_gen = 0;           // generation of the current solve
     unsigned* tri_err = nullptr;    // set by a solve that gave up waiting for a dependency
     int tri_grid = 0;
+
+    // Maxvolume column sweeps (maxvol.cuh); held for the duration of a run
+    double* mv_colscale = nullptr;    // n+m
+    double* mv_colweights = nullptr;  // n+m
+    double* mv_vec = nullptr;         // m: work / btran of the current sweep
+    ipxgpu::Top2* mv_partials = nullptr;
+    ipxgpu::Top2* mv_out = nullptr;
+    unsigned* mv_ticket = nullptr;
+    int mv_grid = 0;
 
     // banded shared-memory sweeps of the normal-matrix apply (may be null)
     ipxgpu::BandDev* band1 = nullptr;  // t = W .* (A'x): gather x, segments = columns

@@ -18,6 +18,7 @@
 #include "split.cuh"
 #include "band_plan.cuh"
 #include "pcr_fused.cuh"
+#include "maxvol.cuh"
 
 namespace ipxgpu {
 
@@ -826,6 +827,8 @@ void ipxgpu_destroy(ipxgpu_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     destroy_split(c);
+    dev_free(c->mv_colscale); dev_free(c->mv_colweights); dev_free(c->mv_vec);
+    dev_free(c->mv_partials); dev_free(c->mv_out); dev_free(c->mv_ticket);
     for (int r = 0; r < c->nranks && r < 16; r++)
         if (r != c->rank && c->peer_base[r] && !c->peers_direct)
             cudaIpcCloseMemHandle(c->peer_base[r]);
@@ -2225,3 +2228,4 @@ int ipxgpu_time_normal_apply(ipxgpu_ctx* c, int reps, int flush_l2, double out_m
 }  // extern "C"
 
 #include "split_api.inc"
+#include "maxvol_api.inc"

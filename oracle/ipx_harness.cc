@@ -26,6 +26,7 @@
 #include "iterate.h"
 #include "kkt_solver_basis.h"
 #include "kkt_solver_diag.h"
+#include "maxvolume.h"
 #include "model.h"
 #include "normal_matrix.h"
 #include "presolver.h"
@@ -435,6 +436,25 @@ ipxint ipxh_kktbasis_solve(void* self, const double* a, const double* b,
     FromVector(vy, y);
     FillInfoOut(h->info, info_out);
     return h->info.errflag;
+}
+
+// Maxvolume on the current basis (src/maxvolume.h:14-15). heuristic != 0: RunHeuristic, else
+// RunSequential. colscale: n+m factors or NULL. out = [errflag, updates, skipped, passes,
+// slices, volinc, time].
+ipxint ipxh_maxvolume(void* self, const double* colscale, ipxint heuristic, double* out) {
+    Harness* h = static_cast<Harness*>(self);
+    Maxvolume maxvol(h->control);
+    Basis& B = GetBasis(h);
+    const Int errflag = heuristic ? maxvol.RunHeuristic(colscale, B)
+                                  : maxvol.RunSequential(colscale, B);
+    out[0] = errflag;
+    out[1] = maxvol.updates();
+    out[2] = maxvol.skipped();
+    out[3] = maxvol.passes();
+    out[4] = maxvol.slices();
+    out[5] = maxvol.volinc();
+    out[6] = maxvol.time();
+    return errflag;
 }
 
 // ---- sparse kernels (src/sparse_matrix.h) on caller-supplied CSC arrays ----

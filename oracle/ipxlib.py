@@ -48,7 +48,7 @@ class IpxLibrary:
         for name in ("ipxh_diag_factorize", "ipxh_kktdiag_factorize", "ipxh_kktdiag_solve",
                      "ipxh_kktdiag_iter", "ipxh_basis_load", "ipxh_basis_from_weights",
                      "ipxh_kktbasis_factorize", "ipxh_kktbasis_solve",
-                     "ipxh_triangular_solve"):
+                     "ipxh_triangular_solve", "ipxh_maxvolume"):
             getattr(L, name).restype = ipxint
         declare_c_api(L)  # the public API, from the same handle (the drop-in build is a dependency)
 
@@ -257,6 +257,15 @@ class IpxModel:
         out = np.zeros(16)
         err = self.lib.ipxh_kktbasis_factorize(self.h, _d(out))
         return dict(zip(INFO_OUT_KEYS, out.tolist()), err=err)
+
+    def maxvolume(self, colscale, heuristic=True):
+        """Maxvolume::RunHeuristic / RunSequential on the current basis (src/maxvolume.h)."""
+        cs = None if colscale is None else _f64(colscale)
+        out = np.zeros(7)
+        err = self.lib.ipxh_maxvolume(self.h, _d(cs) if cs is not None else None,
+                                      ipxint(1 if heuristic else 0), _d(out))
+        keys = ("errflag", "updates", "skipped", "passes", "slices", "volinc", "time")
+        return dict(zip(keys, out.tolist()), err=err)
 
     def kktbasis_solve(self, a, b, tol):
         a, b = _f64(a), _f64(b)

@@ -180,3 +180,56 @@ def kktdiag_solve(m, n, A, W, diag, resscale, a, b, tol, maxiter):
                                   _d(b), C.c_double(tol), oint(maxiter), _d(x), _d(y),
                                   C.byref(it))
     return x, y, {"errflag": int(err), "iter": it.value}
+
+
+# ---- Maxvolume column sweeps (numpy restatement; reference src/maxvolume.cc) ----
+
+def column_dots(AIp, AIi, AIx, x):
+    """AI[:,j]'x for every column, each summed in storage order like DotColumn
+    (reference src/sparse_matrix.h:136-143)."""
+    AIp, AIi = _i64(AIp), _i64(AIi)
+    prod = _f64(x)[AIi] * _f64(AIx)
+    ncol = len(AIp) - 1
+    length = np.diff(AIp)
+    out = np.zeros(ncol)
+    for k in range(int(length.max()) if ncol else 0):
+        sel = np.nonzero(length > k)[0]
+        out[sel] = out[sel] + prod[AIp[sel] + k]
+    return out
+
+
+def find_largest(weights):
+    """FindLargest (reference src/maxvolume.cc:170-200): (jmax2, jmax) of an ascending scan
+    with strict comparisons, both starting at column 0 with weight 0."""
+    w = np.abs(_f64(weights))
+    jmax = jmax2 = 0
+    wmax = wmax2 = 0.0
+    for j in range(len(w)):
+        if w[j] > wmax:
+            wmax2, jmax2 = wmax, jmax
+            wmax, jmax = w[j], j
+        elif w[j] > wmax2:
+            wmax2, jmax2 = w[j], j
+    return jmax2, jmax
+
+
+def maxvol_weights(AIp, AIi, AIx, colscale, work):
+    """Column weights at the top of Maxvolume::Driver (reference src/maxvolume.cc:220-231)."""
+    cs = _f64(colscale)
+    return np.where(cs != 0.0, column_dots(AIp, AIi, AIx, work) * cs, 0.0)
+
+
+def maxvol_update(AIp, AIi, AIx, colscale, colweights, btran, alpha, jb, colscale_jb,
+                  colweight_jb, jn):
+    """Weight update after the exchange of jb and jn (reference src/maxvolume.cc:291-308) with
+    the tableau row of jb over the nonbasic columns from Basis::TableauRow's dense branch
+    (src/basis.cc:266-279); jb is still basic when the row is formed, so its entry is 0."""
+    cs, cw = _f64(colscale).copy(), _f64(colweights).copy()
+    row = np.where(cs != 0.0, column_dots(AIp, AIi, AIx, btran), 0.0)
+    row[jb] = 0.0
+    cs[jb] = colscale_jb
+    cs[jn] = 0.0
+    cw = cw + (alpha * row) * cs
+    cw[jb] = colweight_jb
+    cw[jn] = 0.0
+    return cs, cw
