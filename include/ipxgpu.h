@@ -6,7 +6,7 @@
  *
  * Each entry point replaces one interface of the reference (file:line cited
  * per function). IPX has no FFI/plugin seam for this path; the reference-side
- * binding is link-time substitution of six translation units, shown in
+ * binding is link-time substitution of seven translation units, shown in
  * INTEGRATION.md, whose replacements (ipx_b200/host/*.cc) call exactly these
  * functions.
  *

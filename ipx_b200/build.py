@@ -1,7 +1,7 @@
 """Build recipes for the native parts of ipx_b200 (in-tree, sm_100a only).
 
 * ``ipx_b200/_build/libipxgpu.so``   CUDA kernels + C ABI (include/ipxgpu.h); needs nvcc only.
-* ``ipx_b200/_build/libipx_gpu.so``  IPX with the six hot-path TUs replaced by the GPU
+* ``ipx_b200/_build/libipx_gpu.so``  IPX with seven TUs (the hot path and Maxvolume) replaced by the GPU
   drop-ins of ipx_b200/host; needs the reference tree (compiled against its
   UNMODIFIED headers), so it is built where /root/reference exists and travels
   to the GPU box as a prebuilt file.

@@ -5,7 +5,7 @@
 //   oracle/_ref/libipx_ref.so          with the reference CPU objects (the parity oracle
 //                                      and the CPU baseline), and
 //   oracle/_ref/libipx_gpu_harness.so  alone, against ipx_b200/_build/libipx_gpu.so - the
-//                                      same reference objects EXCEPT the six hot-path TUs,
+//                                      same reference objects EXCEPT the seven substituted TUs,
 //                                      which are replaced by the GPU drop-ins of
 //                                      ipx_b200/host. The product library holds no test code.
 // Tests drive both through identical calls, so a parity test reads like a test
