@@ -242,6 +242,20 @@ int ipxgpu_kktdiag_solve(ipxgpu_ctx* ctx, const double* a, const double* b,
                          ipxgpu_cr_result* result,
                          ipxgpu_interrupt_fn interrupt, void* user);
 
+/* ---- context options ---- */
+
+/* "tri_lt_reference_order" (0 / 1; default 0, or 1 when the environment has
+ * IPXGPU_TRI_LT=reference at context creation): summation order inside a row
+ * of the L' solve (which = 3 below). The reference sums a column of L from the
+ * diagonal downwards (src/sparse_matrix.cc:290-303) while the solve runs
+ * upwards, so the FIRST summand of a row is the dependency that resolves LAST
+ * and a parallel solve must chain every addition of the row after it. 0: the
+ * row is summed in the order its dependencies resolve (bottom up) - the same
+ * sum in the opposite order, a rounding-level difference. 1: the reference's
+ * order; all four solves are then bit-identical to the reference's loops. The
+ * other three solves are bit-identical either way. */
+int ipxgpu_set_option(ipxgpu_ctx* ctx, const char* name, int64_t value);
+
 /* ---- sparse triangular solves (reference src/sparse_matrix.cc:224-311) ---- */
 
 /* Uploads L (strict lower, unit diagonal not stored) and U (upper, diagonal
@@ -344,6 +358,14 @@ int ipxgpu_maxvol_release(ipxgpu_ctx* ctx);
  * (A'x), sweep2 (A t)]. */
 int ipxgpu_time_normal_apply(ipxgpu_ctx* ctx, int reps, int flush_l2,
                              double out_ms[3]);
+/* Mean device time (CUDA events on the context's stream) of `reps` solves
+ * with system `which` (0..3 as in ipxgpu_tri_solve) on a resident copy of x. */
+int ipxgpu_time_tri_solve(ipxgpu_ctx* ctx, int which, int reps, const double* x,
+                          double* out_ms);
+/* Tuning only: with option "tri_trace" = 1 every row of a triangular solve
+ * stamps %globaltimer when its warp starts it and when its value is final;
+ * out receives 2*m stamps [start, finish] of the last solve, by row. */
+int ipxgpu_tri_trace(ipxgpu_ctx* ctx, uint64_t* out);
 /* Host-only check of the banded sweep layout (no device needed): re-tiles the
  * structural columns of AI for both sweeps of the normal-matrix apply with the
  * planner's choice (force != 0: accept any plan that fits), walks the row

@@ -50,7 +50,7 @@ EXPORTS = ("ipxgpu_default_options ipxgpu_last_error ipxgpu_device_count ipxgpu_
            "ipxgpu_kktdiag_solve ipxgpu_lu_load ipxgpu_tri_solve ipxgpu_split_prepare "
            "ipxgpu_split_apply ipxgpu_kktbasis_prepare ipxgpu_basis_solve ipxgpu_kktbasis_solve ipxgpu_time_normal_apply ipxgpu_launch_count ipxgpu_band_selftest ipxgpu_peer_export ipxgpu_peer_import "
            "ipxgpu_maxvol_weights ipxgpu_maxvol_skip ipxgpu_maxvol_update ipxgpu_maxvol_get "
-           "ipxgpu_maxvol_release").split()
+           "ipxgpu_maxvol_release ipxgpu_set_option ipxgpu_time_tri_solve ipxgpu_tri_trace").split()
 
 _lib = None
 
@@ -334,6 +334,9 @@ class Context:
                                               C.cast(None, INTERRUPT_FN), None))
         return x, y, res.asdict()
 
+    def set_option(self, name, value):
+        _check(self.lib.ipxgpu_set_option(self.h, name.encode(), i64(value)))
+
     # ---- Maxvolume column sweeps ----
     def maxvol_weights(self, colscale, work):
         cs, w, top = _f64(colscale), _f64(work), MaxvolTop()
@@ -361,6 +364,17 @@ class Context:
         _check(self.lib.ipxgpu_maxvol_release(self.h))
 
     # ---- measurement ----
+    def time_tri_solve(self, which, x, reps=10):
+        x, out = _f64(x), C.c_double(0.0)
+        _check(self.lib.ipxgpu_time_tri_solve(self.h, C.c_int(which), C.c_int(reps), _d(x),
+                                              C.byref(out)))
+        return out.value
+
+    def tri_trace(self):
+        out = np.zeros(2 * self.m, np.uint64)
+        _check(self.lib.ipxgpu_tri_trace(self.h, out.ctypes.data_as(C.POINTER(C.c_uint64))))
+        return out.reshape(self.m, 2)
+
     def time_normal_apply(self, reps, flush_l2=True):
         out = (C.c_double * 3)()
         _check(self.lib.ipxgpu_time_normal_apply(self.h, C.c_int(reps), C.c_int(1 if flush_l2 else 0),

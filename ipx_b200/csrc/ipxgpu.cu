@@ -836,6 +836,7 @@ void ipxgpu_destroy(ipxgpu_ctx* c) {
     dev_free(c->peer_dev);
     dev_free(c->fused_bar);
     dev_free(c->tri_ll);
+    dev_free(c->tri_trace);
     dev_free(c->xchg_abort);
     dev_free(c->tri_err);
     dev_free(c->fused_tickets);
@@ -1038,6 +1039,8 @@ int ipxgpu_create(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp, co
     cudaDeviceProp prop;
     IPXGPU_CUDA(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
+    if (const char* env = std::getenv("IPXGPU_TRI_LT"))
+        c->tri_lt_reference = std::string(env) == "reference";
     if (opt.stream) {
         c->stream = (cudaStream_t)opt.stream;
     } else {

@@ -48,8 +48,16 @@ struct TriDev {
     int dim = 0;
     int subtract_seq = 0;  // 1: v -= a*x per entry (L, U column sweeps of the
                            // reference); 0: v = x[i] - sum (U', L' row sweeps)
-    int reverse = 0;       // 1: a row's entries resolve back to front (L': the reference sums
-                           // a column of L from the diagonal downwards, the solve runs upwards)
+    int reverse = 0;       // a row's entries resolve back to front (L': the reference sums a
+                           // column of L from the diagonal downwards, the solve runs upwards).
+                           // 1: summed front to back all the same (the reference's order, a
+                           // serial chain of additions AFTER the last dependency arrived);
+                           // 2: summed back to front, in the order the dependencies resolve
+    int prefix = 1;        // fold what precedes a chunk's first missing entry before waiting
+    int mailbox = 1;       // rows solved by a warp of the same CTA are read from shared memory
+    unsigned pause_cap = 32;   // longest pause (ns) between two rounds of looks at global records
+    unsigned long long* trace = nullptr;  // tuning only: [2*dim] globaltimer at row start / finish
+    int* pos = nullptr;    // [dim] position of row i in `order` (inverse permutation)
     int* ptr = nullptr;    // [dim+1] off-diagonal entries of row i
     int* idx = nullptr;
     double* val = nullptr;
@@ -162,13 +170,63 @@ __device__ __forceinline__ void tri_ll_store(ulonglong2* p, unsigned gen, double
 // a 1000-entry row of a dense trailing block paid all its memory round trips after that.
 constexpr int kTriBatch = 8;
 constexpr int kTriStash = 2048;  // parked products per warp (16 KB)
+constexpr int kTriMailDepth = 8; // records per warp in the CTA's shared-memory mailbox
+
+// Mailbox of a CTA: the last kTriMailDepth rows each of its warps solved, as self-validating
+// records {round+1 : 32 | half of x} x 2 in shared memory. Row positions are dealt round robin
+// over the grid's warps, so a dependency chain (one row per level) runs through the 12 warps of
+// a CTA before it moves to the next CTA: 11 of 12 links can be handed over through shared memory
+// (tens of cycles) instead of an L2 round trip. The global record is always written as well; a
+// reader that finds its slot overwritten (the producer is kTriMailDepth rounds ahead) takes
+// that one.
+__device__ __forceinline__ void tri_mail_store(ulonglong2* slot, unsigned tag, double v) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    ulonglong2 rec;
+    rec.x = ((unsigned long long)tag << 32) | (bits & 0xffffffffull);
+    rec.y = ((unsigned long long)tag << 32) | (bits >> 32);
+    *reinterpret_cast<volatile unsigned long long*>(&slot->x) = rec.x;
+    *reinterpret_cast<volatile unsigned long long*>(&slot->y) = rec.y;
+}
+// 1: value read, 0: not there yet, -1: overwritten by a later round (take the global record)
+__device__ __forceinline__ int tri_mail_load(const ulonglong2* slot, unsigned tag, double* val) {
+    const unsigned long long w0 = *reinterpret_cast<const volatile unsigned long long*>(&slot->x);
+    const unsigned long long w1 = *reinterpret_cast<const volatile unsigned long long*>(&slot->y);
+    const unsigned t0 = (unsigned)(w0 >> 32), t1 = (unsigned)(w1 >> 32);
+    if (t0 == tag && t1 == tag) {
+        *val = __longlong_as_double((long long)(((w1 & 0xffffffffull) << 32) | (w0 & 0xffffffffull)));
+        return 1;
+    }
+    return (t0 > tag || t1 > tag) ? -1 : 0;
+}
+
+// Folds lanes [lo, hi) of `prod` into the running value, lane after lane (sub: v -= p, else
+// v += p); down: from hi-1 to lo. The bounds are uniform over the warp. All 32 shuffles go out
+// back to back and only the chain of additions stays serial (a rolled loop pays shuffle latency
+// + add per entry); lanes outside [lo, hi) are skipped by predication.
+__device__ __forceinline__ double tri_fold(double v, double prod, int lo, int hi, bool sub,
+                                           bool down) {
+    const double sp = sub ? -prod : prod;  // v - p == v + (-p) exactly
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+        const int kk = down ? 31 - k : k;
+        const double p = __shfl_sync(0xffffffffu, sp, kk);
+        if (kk >= lo && kk < hi) v = v + p;
+    }
+    return v;
+}
 
 __device__ __forceinline__ void tri_row_warp(const TriDev& T, int i, double* x, ulonglong2* ll,
-                                             unsigned gen, int lane, double* stash, unsigned* err) {
+                                             unsigned gen, int lane, double* stash, unsigned* err,
+                                             ulonglong2* mail, int nwarps, int warp, int round) {
     const int b = T.ptr[i], e = T.ptr[i + 1];
+    const bool sub = T.subtract_seq != 0;
+    const bool down = T.reverse == 2;  // pieces, chunks and lanes from the back
+    if (T.trace != nullptr && lane == 0) T.trace[2 * i] = globaltimer();
     double v = __ldcg(x + i);
     double d = 0.0;
-    for (int q0 = b; q0 < e; q0 += kTriStash) {
+    const int npieces = (e - b + kTriStash - 1) / kTriStash;
+    for (int pc = 0; pc < npieces; pc++) {
+        const int q0 = b + (down ? npieces - 1 - pc : pc) * kTriStash;
         const int qe = min(e, q0 + kTriStash);
         unsigned long long mypend = 0ull;  // bit c: my entry of chunk c was not ready in phase A
         for (int p0 = q0; p0 < qe; p0 += 32 * kTriBatch) {
@@ -203,37 +261,73 @@ __device__ __forceinline__ void tri_row_warp(const TriDev& T, int i, double* x, 
             if (__ballot_sync(0xffffffffu, mine) == 0u) return prod;
             int jj = 0;
             double aa = 0.0;
+            const ulonglong2* slot = nullptr;  // mailbox slot of a row solved in this CTA
+            unsigned want = 0;
             if (mine) {
                 jj = __ldg(T.idx + q0 + 32 * c + lane);
                 aa = __ldg(T.val + q0 + 32 * c + lane);
+                if (mail != nullptr) {
+                    // position p of the order is solved by warp p % nwarps in its round p / nwarps
+                    const int pj = __ldg(T.pos + jj);
+                    const int g = pj % nwarps, rj = pj / nwarps;
+                    if (g / kTriWarps == (int)blockIdx.x) {
+                        slot = mail + (g % kTriWarps) * kTriMailDepth + (rj % kTriMailDepth);
+                        want = (unsigned)rj + 1u;
+                    }
+                }
             }
             bool ok = !mine;
             double xj = 0.0;
-            unsigned pause = 0;
-            for (;;) {
-                if (!ok) ok = tri_ll_load(ll + jj, gen, &xj);
-                const unsigned pending = __ballot_sync(0xffffffffu, !ok);
-                if (pending == 0u) break;
-                if (lane == __ffs(pending) - 1) {
-                    unsigned spins = 0;
-                    while (!tri_ll_load(ll + jj, gen, &xj)) {
-                        if (pause) __nanosleep(pause);
-                        pause = min(2 * pause + 32u, 256u);
-                        // A dependency that never resolves (cannot happen with a valid level
-                        // order) must not hang the GPU: give up after ~2 s and flag the solve.
-                        if (++spins > (1u << 23)) {
-                            *err = 1u;
-                            break;
-                        }
-                    }
-                    ok = true;
+            // one look: the mailbox where the row is this CTA's, the global record otherwise
+            auto look = [&]() -> bool {
+                if (slot != nullptr) {
+                    const int r = tri_mail_load(slot, want, &xj);
+                    if (r > 0) return true;
+                    if (r == 0) return false;
+                    slot = nullptr;  // overwritten: the global record is there
                 }
-                __syncwarp();
+                return tri_ll_load(ll + jj, gen, &xj);
+            };
+            // All lanes that miss an entry look together, then round after round the first few
+            // of those still missing: entries arrive in lane order at the head of a dependency
+            // chain, and in batches where a level is wide. An entry is seen within one L2 round
+            // trip of its arrival, entries that arrived together cost one round trip, and a
+            // waiting warp keeps at most `window` looks in flight - hundreds of warps wait for
+            // the same few records at the head of a chain. (Round 1 let only the first missing
+            // lane poll, after a look by all: two round trips per hop, tools/tri_trace.py.)
+            unsigned pause = 0, spins = 0;
+            int window = 4;
+            if (!ok) ok = look();
+            unsigned pending = __ballot_sync(0xffffffffu, !ok);
+            while (pending != 0u) {
+                // the window sits where the next arrivals are: at the lowest missing lanes, or
+                // at the highest ones where the row is summed from the back
+                const int first = __ffs(pending) - 1, last = 31 - __clz(pending);
+                const bool in_window = T.reverse != 0 ? lane > last - window : lane < first + window;
+                if (!ok && in_window) ok = look();
+                const unsigned now = __ballot_sync(0xffffffffu, !ok);
+                // the whole window arrived at once: a batch, look at twice as many next time
+                const unsigned win_mask = __ballot_sync(0xffffffffu, in_window);
+                if ((now & win_mask) == 0u) {
+                    window = min(2 * window, 32);
+                    pause = 0;
+                } else if (now == pending) {
+                    if (pause) __nanosleep(pause);
+                    pause = min(2 * pause + 16u, T.pause_cap);
+                    window = 4;
+                }
+                pending = now;
+                // A dependency that never resolves (cannot happen with a valid level order) must
+                // not hang the GPU: give up after ~2 s and flag the solve.
+                if (++spins > (1u << 23)) {
+                    if (lane == 0) *err = 1u;
+                    break;
+                }
             }
             if (mine) prod = __dmul_rn(aa, xj);
             return prod;
         };
-        if (T.reverse) {
+        if (T.reverse == 1) {
             // The dependencies of the LAST chunk resolve first (see above): wait for the
             // chunks back to front and park the products, then sum front to back.
             for (int c = nchunks - 1; c >= 0; c--) {
@@ -242,33 +336,41 @@ __device__ __forceinline__ void tri_row_warp(const TriDev& T, int i, double* x, 
             }
             mypend = 0ull;
         }
-        for (int c = 0; c < nchunks; c++) {
+        for (int cc = 0; cc < nchunks; cc++) {
+            const int c = down ? nchunks - 1 - cc : cc;
             const int cnt = min(32, qe - (q0 + 32 * c));
-            const double prod = resolve(c, stash[c * 32 + lane]);
-            // Full chunks unrolled: the 32 shuffles go out back to back and only the chain of
-            // additions stays serial (a rolled loop pays shuffle latency + add per entry).
-            if (T.subtract_seq) {
-                if (cnt == 32) {
-#pragma unroll
-                    for (int k = 0; k < 32; k++) v = v - __shfl_sync(0xffffffffu, prod, k);
-                } else {
-                    for (int k = 0; k < cnt; k++) v = v - __shfl_sync(0xffffffffu, prod, k);
-                }
+            double prod = stash[c * 32 + lane];
+            double acc = sub ? v : d;
+            const unsigned missing = __ballot_sync(0xffffffffu, (mypend >> c) & 1ull);
+            if (missing == 0u) {
+                acc = tri_fold(acc, prod, 0, cnt, sub, down);
+            } else if (!T.prefix) {
+                prod = resolve(c, prod);
+                acc = tri_fold(acc, prod, 0, cnt, sub, down);
+            } else if (!down) {
+                // what precedes the first missing entry is folded while it is awaited
+                const int first = __ffs(missing) - 1;
+                acc = tri_fold(acc, prod, 0, first, sub, false);
+                prod = resolve(c, prod);
+                acc = tri_fold(acc, prod, first, cnt, sub, false);
             } else {
-                if (cnt == 32) {
-#pragma unroll
-                    for (int k = 0; k < 32; k++) d = d + __shfl_sync(0xffffffffu, prod, k);
-                } else {
-                    for (int k = 0; k < cnt; k++) d = d + __shfl_sync(0xffffffffu, prod, k);
-                }
+                const int last = 31 - __clz(missing);
+                acc = tri_fold(acc, prod, last + 1, cnt, sub, true);
+                prod = resolve(c, prod);
+                acc = tri_fold(acc, prod, 0, last + 1, sub, true);
             }
+            if (sub) v = acc; else d = acc;
         }
     }
-    if (!T.subtract_seq) v = v - d;
+    if (!sub) v = v - d;
     if (T.diag) v = v / __ldg(T.diag + i);
     if (lane == 0) {
         tri_ll_store(ll + i, gen, v);  // what the dependent rows read
+        if (mail != nullptr)
+            tri_mail_store(mail + warp * kTriMailDepth + (round % kTriMailDepth),
+                           (unsigned)round + 1u, v);
         x[i] = v;                      // the result
+        if (T.trace != nullptr) T.trace[2 * i + 1] = globaltimer();
     }
 }
 
@@ -276,14 +378,22 @@ __device__ __forceinline__ void tri_row_warp(const TriDev& T, int i, double* x, 
 __global__ void __launch_bounds__(kTriWarps * 32, 1)
 tri_syncfree_kernel(TriDev T, double* x, ulonglong2* ll, unsigned gen, unsigned* err,
                     const CrState* st) {
-    extern __shared__ __align__(16) double tri_stash[];  // kTriWarps * kTriStash
+    extern __shared__ __align__(16) double tri_stash[];  // kTriWarps * kTriStash, then the mailbox
     if (st && st->done) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int gwarp = blockIdx.x * kTriWarps + warp;
     const int nwarps = gridDim.x * kTriWarps;
     double* stash = tri_stash + (size_t)warp * kTriStash;
-    for (int r = gwarp; r < T.dim; r += nwarps)
-        tri_row_warp(T, T.order[r], x, ll, gen, lane, stash, err);
+    ulonglong2* mail = nullptr;
+    if (T.mailbox) {
+        mail = reinterpret_cast<ulonglong2*>(tri_stash + (size_t)kTriWarps * kTriStash);
+        for (int k = threadIdx.x; k < kTriWarps * kTriMailDepth; k += kTriWarps * 32)
+            mail[k] = make_ulonglong2(0ull, 0ull);
+        __syncthreads();
+    }
+    int round = 0;
+    for (int r = gwarp; r < T.dim; r += nwarps, round++)
+        tri_row_warp(T, T.order[r], x, ll, gen, lane, stash, err, mail, nwarps, warp, round);
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -412,12 +522,18 @@ static int ensure_reduce(ipxgpu_ctx* c, int grid);
 static int launch_normal_apply_w(ipxgpu_ctx* c, const double* Wc, const double* Ws,
                                  const double* x, double* y, int mode, int slot, CrState* st);
 
+static int env_flag(const char* name, int dflt) {
+    const char* env = std::getenv(name);
+    return env ? std::atoi(env) : dflt;
+}
+
 static void free_tri(TriSystem* T) {
     dev_free(T->d.ptr);
     dev_free(T->d.idx);
     dev_free(T->d.val);
     dev_free(T->d.diag);
     dev_free(T->d.order);
+    dev_free(T->d.pos);
     dev_free(T->d.level_ptr);
     T->steps.clear();
     T->nlevels = 0;
@@ -491,9 +607,19 @@ static int build_tri(ipxgpu_ctx* c, TriSystem* T, int dim, const std::vector<int
     IPXGPU_TRY(upload(&T->d.val, val, s));
     if (diag) IPXGPU_TRY(upload(&T->d.diag, *diag, s));
     IPXGPU_TRY(upload(&T->d.order, order, s));
+    {
+        std::vector<int> pos(dim);
+        for (int r = 0; r < dim; r++) pos[order[r]] = r;
+        IPXGPU_TRY(upload(&T->d.pos, pos, s));
+    }
     IPXGPU_TRY(upload(&T->d.level_ptr, lptr, s));
     IPXGPU_CUDA(cudaStreamSynchronize(s));
     return IPXGPU_OK;
+}
+
+static size_t tri_smem_bytes() {
+    return (size_t)kTriWarps * kTriStash * sizeof(double) +
+           (size_t)kTriWarps * kTriMailDepth * sizeof(ulonglong2);
 }
 
 static int launch_tri(ipxgpu_ctx* c, const TriSystem& T, double* x, const CrState* st) {
@@ -504,7 +630,7 @@ static int launch_tri(ipxgpu_ctx* c, const TriSystem& T, double* x, const CrStat
     if (!legacy) {
         if (T.d.dim == 0) return IPXGPU_OK;
         if (c->tri_grid == 0) {
-            const size_t smem = (size_t)kTriWarps * kTriStash * sizeof(double);
+            const size_t smem = tri_smem_bytes();
             IPXGPU_CUDA(cudaFuncSetAttribute(tri_syncfree_kernel,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             int per_sm = 0;
@@ -524,6 +650,16 @@ static int launch_tri(ipxgpu_ctx* c, const TriSystem& T, double* x, const CrStat
         }
         const int grid = std::max(1, std::min(c->tri_grid, (T.d.dim + kTriWarps - 1) / kTriWarps));
         TriDev d = T.d;
+        // tuning switches (defaults: on); the summation order of the L' solve is a context
+        // option (ipxgpu_set_option "tri_lt_reference_order")
+        static const int sw_prefix = env_flag("IPXGPU_TRI_PREFIX", 1);
+        static const int sw_mailbox = env_flag("IPXGPU_TRI_MAILBOX", 1);
+        static const int sw_pause = env_flag("IPXGPU_TRI_PAUSE", 32);
+        d.prefix = sw_prefix;
+        d.mailbox = sw_mailbox;
+        d.pause_cap = (unsigned)std::max(0, sw_pause);
+        d.trace = c->tri_trace;
+        if (d.reverse) d.reverse = c->tri_lt_reference ? 1 : 2;
         double* xp = x;
         ulonglong2* ll = c->tri_ll;
         unsigned gen = c->tri_gen;
@@ -531,8 +667,7 @@ static int launch_tri(ipxgpu_ctx* c, const TriSystem& T, double* x, const CrStat
         const CrState* stp = st;
         void* args[] = {&d, &xp, &ll, &gen, &err, &stp};
         IPXGPU_CUDA(cudaLaunchCooperativeKernel((void*)tri_syncfree_kernel, dim3(grid),
-                                                dim3(kTriWarps * 32), args,
-                                                (size_t)kTriWarps * kTriStash * sizeof(double),
+                                                dim3(kTriWarps * 32), args, tri_smem_bytes(),
                                                 c->stream));
         c->launches++;
         return IPXGPU_OK;

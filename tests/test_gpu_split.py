@@ -64,13 +64,30 @@ def test_triangular_solves_bit_exact(capi, oracle, dim, band, seed):
         2: oracle.triangular_solve(dim, Uo, x, "t", "u", 0)[0],
         3: oracle.triangular_solve(dim, Lo, x, "t", "l", 1)[0],
     }
-    for which in range(4):
+    # L, U, U': the rows are summed in the reference's order whatever the options say. L': in the
+    # reference's order with the option below (bit-identical), bottom up by default - the same
+    # sums in the opposite order, so the bar is what one ulp in the right-hand side does to the
+    # reference's own solve.
+    x_ulp = x + np.spacing(np.abs(x)) * np.random.default_rng(seed + 1).choice([-1.0, 1.0], dim)
+    lt_ulp = oracle.triangular_solve(dim, Lo, x_ulp, "t", "l", 1)[0]
+    lt_bar = 100 * np.abs(lt_ulp - expect[3]).max() + 1e-14 * np.abs(expect[3]).max()
+    for which in range(3):
         got = ctx.tri_solve(which, x)
         assert np.array_equal(got, expect[which]), f"solve {which}"
+    got = ctx.tri_solve(3, x)
+    assert np.abs(got - expect[3]).max() <= lt_bar
+    assert np.array_equal(ctx.tri_solve(3, x), got)  # deterministic
     fwd = oracle.triangular_solve(dim, Uo, expect[0], "n", "u", 0)[0]
     bwd = oracle.triangular_solve(dim, Lo, expect[2], "t", "l", 1)[0]
     assert np.array_equal(ctx.tri_solve(4, x), fwd)
+    assert np.abs(ctx.tri_solve(5, x) - bwd).max() <= 100 * np.abs(
+        oracle.triangular_solve(dim, Lo, oracle.triangular_solve(dim, Uo, x_ulp, "t", "u", 0)[0],
+                                "t", "l", 1)[0] - bwd).max() + 1e-14 * np.abs(bwd).max()
+    ctx.set_option("tri_lt_reference_order", 1)
+    assert np.array_equal(ctx.tri_solve(3, x), expect[3]), "solve 3, reference order"
     assert np.array_equal(ctx.tri_solve(5, x), bwd)
+    with pytest.raises(capi.IpxGpuError):
+        ctx.set_option("no_such_option", 1)
     ctx.close()
 
 
