@@ -200,17 +200,30 @@ __device__ __forceinline__ int tri_mail_load(const ulonglong2* slot, unsigned ta
 }
 
 // Folds lanes [lo, hi) of `prod` into the running value, lane after lane (sub: v -= p, else
-// v += p); down: from hi-1 to lo. The bounds are uniform over the warp. All 32 shuffles go out
-// back to back and only the chain of additions stays serial (a rolled loop pays shuffle latency
-// + add per entry); lanes outside [lo, hi) are skipped by predication.
+// v += p); down: from hi-1 to lo. The bounds are uniform over the warp. The shuffles of a group go
+// out back to back and only the chain of additions stays serial (a rolled loop pays shuffle
+// latency + add per entry). Lanes beyond hi contribute -0.0, the one addend that leaves every
+// value - both zeros included - as it is: no select sits on the chain of additions, and the few
+// entries that remain after a row's last dependency arrived cost a few additions, not 32.
 __device__ __forceinline__ double tri_fold(double v, double prod, int lo, int hi, bool sub,
                                            bool down) {
     const double sp = sub ? -prod : prod;  // v - p == v + (-p) exactly
+    if (lo == 0 && hi == 32) {
 #pragma unroll
-    for (int k = 0; k < 32; k++) {
-        const int kk = down ? 31 - k : k;
-        const double p = __shfl_sync(0xffffffffu, sp, kk);
-        if (kk >= lo && kk < hi) v = v + p;
+        for (int k = 0; k < 32; k++) v = v + __shfl_sync(0xffffffffu, sp, down ? 31 - k : k);
+        return v;
+    }
+    for (int k0 = lo; k0 < hi; k0 += 8) {
+        double p[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int kk = k0 + u;
+            const int src = down ? hi - 1 - (kk - lo) : kk;
+            p[u] = __shfl_sync(0xffffffffu, sp, src & 31);
+            if (kk >= hi) p[u] = -0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) v = v + p[u];
     }
     return v;
 }
