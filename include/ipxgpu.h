@@ -244,16 +244,21 @@ int ipxgpu_kktdiag_solve(ipxgpu_ctx* ctx, const double* a, const double* b,
 
 /* ---- context options ---- */
 
-/* "tri_lt_reference_order" (0 / 1; default 0, or 1 when the environment has
- * IPXGPU_TRI_LT=reference at context creation): summation order inside a row
- * of the L' solve (which = 3 below). The reference sums a column of L from the
- * diagonal downwards (src/sparse_matrix.cc:290-303) while the solve runs
- * upwards, so the FIRST summand of a row is the dependency that resolves LAST
- * and a parallel solve must chain every addition of the row after it. 0: the
- * row is summed in the order its dependencies resolve (bottom up) - the same
- * sum in the opposite order, a rounding-level difference. 1: the reference's
- * order; all four solves are then bit-identical to the reference's loops. The
- * other three solves are bit-identical either way. */
+/* "tri_reference_order" (0 / 1; default 0, or 1 when the environment has
+ * IPXGPU_TRI_ORDER=reference at context creation): summation order inside a
+ * row of the triangular solves. 1: the reference's order throughout; all four
+ * solves are bit-identical to the reference's loops. 0 deviates in two places,
+ * both rounding-level differences (the same terms in another order):
+ *  - L' solve (which = 3 below): the reference sums a column of L from the
+ *    diagonal downwards (src/sparse_matrix.cc:290-303) while the solve runs
+ *    upwards, so the FIRST summand of a row is the dependency that resolves
+ *    LAST and every addition of the row has to wait for it; with 0 the row is
+ *    summed in the order its dependencies resolve (bottom up);
+ *  - rows with more than 2048 entries (any system): a serial chain of fp64
+ *    additions advances by one entry every ~14 cycles on the device, so all
+ *    entries but the last 2048 (in summation order) are summed as 32
+ *    interleaved partial sums that are then folded in lane order.
+ * Rows of L, U and U' with up to 2048 entries are bit-identical either way. */
 int ipxgpu_set_option(ipxgpu_ctx* ctx, const char* name, int64_t value);
 
 /* ---- sparse triangular solves (reference src/sparse_matrix.cc:224-311) ---- */

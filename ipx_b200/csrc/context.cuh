@@ -172,7 +172,7 @@ struct ipxgpu_ctx {
     unsigned* tri_err = nullptr;    // set by a solve that gave up waiting for a dependency
     int tri_grid = 0;
     unsigned long long* tri_trace = nullptr;  // tuning only (option "tri_trace")
-    int tri_lt_reference = 0;       // L' solve: 1 = sum a row in the reference's order (option)
+    int tri_reference_order = 0;       // triangular solves: 1 = reference's summation order (option)
 
     // Maxvolume column sweeps (maxvol.cuh); held for the duration of a run
     double* mv_colscale = nullptr;    // n+m

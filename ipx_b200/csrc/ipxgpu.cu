@@ -1039,8 +1039,8 @@ int ipxgpu_create(ipxgpu_ctx** out, int64_t m, int64_t n, const int64_t* AIp, co
     cudaDeviceProp prop;
     IPXGPU_CUDA(cudaGetDeviceProperties(&prop, device));
     c->num_sms = prop.multiProcessorCount;
-    if (const char* env = std::getenv("IPXGPU_TRI_LT"))
-        c->tri_lt_reference = std::string(env) == "reference";
+    if (const char* env = std::getenv("IPXGPU_TRI_ORDER"))
+        c->tri_reference_order = std::string(env) == "reference";
     if (opt.stream) {
         c->stream = (cudaStream_t)opt.stream;
     } else {

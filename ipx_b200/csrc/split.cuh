@@ -54,6 +54,9 @@ struct TriDev {
                            // serial chain of additions AFTER the last dependency arrived);
                            // 2: summed back to front, in the order the dependencies resolve
     int prefix = 1;        // fold what precedes a chunk's first missing entry before waiting
+    int lane_sums = 1;     // rows longer than kTriStash entries: all pieces but the one whose
+                           // dependencies resolve last are summed per lane (32 partial sums,
+                           // folded in lane order) instead of entry by entry; 0: reference order
     int mailbox = 1;       // rows solved by a warp of the same CTA are read from shared memory
     unsigned pause_cap = 32;   // longest pause (ns) between two rounds of looks at global records
     unsigned long long* trace = nullptr;  // tuning only: [2*dim] globaltimer at row start / finish
@@ -238,6 +241,8 @@ __device__ __forceinline__ void tri_row_warp(const TriDev& T, int i, double* x, 
     double v = __ldcg(x + i);
     double d = 0.0;
     const int npieces = (e - b + kTriStash - 1) / kTriStash;
+    const bool lanesum = T.lane_sums != 0 && T.reverse != 1 && npieces > 1;
+    double part = 0.0;  // lanesum: this lane's share of the pieces before the last one
     for (int pc = 0; pc < npieces; pc++) {
         const int q0 = b + (down ? npieces - 1 - pc : pc) * kTriStash;
         const int qe = min(e, q0 + kTriStash);
@@ -340,6 +345,23 @@ __device__ __forceinline__ void tri_row_warp(const TriDev& T, int i, double* x, 
             if (mine) prod = __dmul_rn(aa, xj);
             return prod;
         };
+        if (lanesum && pc < npieces - 1) {
+            // A serial chain of fp64 additions advances by one entry every ~14 cycles: a
+            // linking row of a block-angular basis with 40,000 entries holds everything that
+            // depends on it for 300 us (the CPU needs 50). Here every lane sums its own entries
+            // of the piece, 64 additions deep.
+            for (int c = 0; c < nchunks; c++) {
+                double prod = stash[c * 32 + lane];
+                if (__ballot_sync(0xffffffffu, (mypend >> c) & 1ull) != 0u) prod = resolve(c, prod);
+                part = part + prod;
+            }
+            continue;
+        }
+        if (lanesum) {
+            // the last piece (in the order of the sum): first the 32 partial sums, lane by lane
+            if (sub) v = tri_fold(v, part, 0, 32, true, false);
+            else d = tri_fold(d, part, 0, 32, false, false);
+        }
         if (T.reverse == 1) {
             // The dependencies of the LAST chunk resolve first (see above): wait for the
             // chunks back to front and park the products, then sum front to back.
@@ -663,8 +685,8 @@ static int launch_tri(ipxgpu_ctx* c, const TriSystem& T, double* x, const CrStat
         }
         const int grid = std::max(1, std::min(c->tri_grid, (T.d.dim + kTriWarps - 1) / kTriWarps));
         TriDev d = T.d;
-        // tuning switches (defaults: on); the summation order of the L' solve is a context
-        // option (ipxgpu_set_option "tri_lt_reference_order")
+        // tuning switches (defaults: on); the summation order of L' rows and of long rows is
+        // a context option (ipxgpu_set_option "tri_reference_order")
         static const int sw_prefix = env_flag("IPXGPU_TRI_PREFIX", 1);
         static const int sw_mailbox = env_flag("IPXGPU_TRI_MAILBOX", 1);
         static const int sw_pause = env_flag("IPXGPU_TRI_PAUSE", 32);
@@ -672,7 +694,8 @@ static int launch_tri(ipxgpu_ctx* c, const TriSystem& T, double* x, const CrStat
         d.mailbox = sw_mailbox;
         d.pause_cap = (unsigned)std::max(0, sw_pause);
         d.trace = c->tri_trace;
-        if (d.reverse) d.reverse = c->tri_lt_reference ? 1 : 2;
+        if (d.reverse) d.reverse = c->tri_reference_order ? 1 : 2;
+        d.lane_sums = c->tri_reference_order ? 0 : 1;
         double* xp = x;
         ulonglong2* ll = c->tri_ll;
         unsigned gen = c->tri_gen;

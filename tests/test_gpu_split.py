@@ -83,11 +83,52 @@ def test_triangular_solves_bit_exact(capi, oracle, dim, band, seed):
     assert np.abs(ctx.tri_solve(5, x) - bwd).max() <= 100 * np.abs(
         oracle.triangular_solve(dim, Lo, oracle.triangular_solve(dim, Uo, x_ulp, "t", "u", 0)[0],
                                 "t", "l", 1)[0] - bwd).max() + 1e-14 * np.abs(bwd).max()
-    ctx.set_option("tri_lt_reference_order", 1)
+    ctx.set_option("tri_reference_order", 1)
     assert np.array_equal(ctx.tri_solve(3, x), expect[3]), "solve 3, reference order"
     assert np.array_equal(ctx.tri_solve(5, x), bwd)
     with pytest.raises(capi.IpxGpuError):
         ctx.set_option("no_such_option", 1)
+    ctx.close()
+
+
+def test_triangular_solves_long_rows(capi, oracle):
+    """Rows with more than 2048 entries (linking rows of a block-angular basis): summed as 32
+    interleaved partial sums by default - a rounding-level difference, held to what one ulp in the
+    right-hand side does to the oracle's own solve - and entry by entry, bit for bit, with the
+    option tri_reference_order."""
+    dim = 6000
+    rng = np.random.default_rng(77)
+    Lm = sp.random(dim, dim, density=2e-3, random_state=rng.integers(1 << 30), format="lil",
+                   data_rvs=lambda k: rng.uniform(-0.9, 0.9, k))
+    Lm[:, 0] = rng.uniform(-0.01, 0.01, (dim, 1))      # long row 0 of the L' solve
+    Lm[dim - 1, :] = rng.uniform(-0.01, 0.01, (1, dim))  # long last row of the L solve
+    Lm = sp.tril(Lm.tocsc(), -1).tocsc()
+    Um = sp.random(dim, dim, density=2e-3, random_state=rng.integers(1 << 30), format="lil",
+                   data_rvs=lambda k: rng.uniform(-0.9, 0.9, k))
+    Um[0, :] = rng.uniform(-0.01, 0.01, (1, dim))        # long row 0 of the U solve
+    Um[:, dim - 1] = rng.uniform(-0.01, 0.01, (dim, 1))  # long last row of the U' solve
+    Um = (sp.triu(Um.tocsc(), 1) + sp.diags(rng.uniform(1.0, 3.0, dim))).tocsc()
+    for M in (Lm, Um):
+        M.sort_indices()
+    L = (Lm.indptr.astype(np.int64), Lm.indices.astype(np.int64), Lm.data.copy())
+    U = (Um.indptr.astype(np.int64), Um.indices.astype(np.int64), Um.data.copy())
+    lp = lpgen.random_sparse_lp(dim, 2 * dim, 3, 78)
+    ctx = capi.Context(lp.m, lp.n, *lp.solver_form())
+    ctx.lu_load(L, U)
+    Lo, Uo = oracle.Csc(*L), oracle.Csc(*U)
+    x = rng.standard_normal(dim)
+    x_ulp = x + np.spacing(np.abs(x)) * rng.choice([-1.0, 1.0], dim)
+    systems = [(Lo, "n", "l", 1), (Uo, "n", "u", 0), (Uo, "t", "u", 0), (Lo, "t", "l", 1)]
+    want = [oracle.triangular_solve(dim, A, x, t, ul, unit)[0] for A, t, ul, unit in systems]
+    moved = [oracle.triangular_solve(dim, A, x_ulp, t, ul, unit)[0] for A, t, ul, unit in systems]
+    for which in range(4):
+        got = ctx.tri_solve(which, x)
+        bar = 100 * np.abs(moved[which] - want[which]).max() + 1e-13 * np.abs(want[which]).max()
+        assert np.abs(got - want[which]).max() <= bar, which
+        assert np.array_equal(ctx.tri_solve(which, x), got)  # deterministic
+    ctx.set_option("tri_reference_order", 1)
+    for which in range(4):
+        assert np.array_equal(ctx.tri_solve(which, x), want[which]), which
     ctx.close()
 
 
