@@ -31,6 +31,16 @@ def _solve(lp, ngpus, tmp_path, *extra):
         return json.load(f)["results"]["gpu"]
 
 
+def _band(lp):
+    """The reference's own runs on this LP: generator order, other column orders, one-ulp copies
+    (tests/golden/make_group_golden.py)."""
+    path = os.path.join(REPO, "tests", "golden", "e2e_group_bands.json")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/e2e_group_bands.json missing (tests/golden/make_group_golden.py)")
+    with open(path) as f:
+        return json.load(f)[lp]["runs"]
+
+
 @pytest.mark.parametrize("lp,extra", [
     ("random:20000:200000:8", ("--stop-at-switch", "-1", "--crossover", "0")),
     ("random:500:5000:10", ()),          # both phases and crossover: the basis phase is single-GPU
@@ -39,15 +49,25 @@ def _solve(lp, ngpus, tmp_path, *extra):
 def test_lp_solver_on_two_gpus_matches_one(lp, extra, tmp_path):
     if _gpus() < 2:
         pytest.skip("needs 2 GPUs")
+    ref = _band(lp)
     one = _solve(lp, 1, tmp_path, *extra)
     two = _solve(lp, 2, tmp_path, *extra)
-    assert one["status"] == two["status"] and one["status_ipm"] == two["status_ipm"]
-    assert one["status_crossover"] == two["status_crossover"]
-    assert abs(one["iter"] - two["iter"]) <= 1
+    # The bar is the reference, not the other arm: IPM iterations within +-1 of what the
+    # reference's own runs span (the same LP with its columns in another order, or with one-ulp
+    # changes, takes 13 or 14 iterations at 500 x 5000: a Newton solve there ends within rounding
+    # of its tolerance, and which side it lands on decides the path), same status, objective to
+    # 1e-9 of the reference's.
+    iters = [r["iter"] for r in ref]
+    for arm in (one, two):
+        assert arm["status"] == ref[0]["status"] and arm["status_ipm"] == ref[0]["status_ipm"]
+        assert arm["status_crossover"] == ref[0]["status_crossover"]
+        assert min(iters) - 1 <= arm["iter"] <= max(iters) + 1, (arm["iter"], iters)
+        if ref[0]["status"] == 1000:
+            assert abs(arm["objval"] - ref[0]["objval"]) <= 1e-9 * max(1.0, abs(ref[0]["objval"]))
     # the sharded solve sums the ranks' partial products in rank order: rounding-level
-    # differences only, so the early iterations agree line by line
-    for a, b in zip(one["per_iter"][:4], two["per_iter"][:4]):
+    # differences only, so the early iterations agree line by line - with each other and with
+    # the reference's CR counts
+    for k, (a, b) in enumerate(zip(one["per_iter"][:4], two["per_iter"][:4])):
         assert a["kktiter"] == b["kktiter"] and a["mu"] == b["mu"], (a, b)
-    if one["status"] == 1000:
-        assert abs(one["objval"] - two["objval"]) <= 1e-9 * max(1.0, abs(one["objval"]))
+        assert a["kktiter"] == ref[0]["kktiter_per_iter"][k], (k, a, ref[0]["kktiter_per_iter"])
     assert two["kktiter1"] > 0 and two["time_cr1"] > 0
