@@ -354,6 +354,20 @@ int ipxgpu_maxvol_get(ipxgpu_ctx* ctx, double* colscale, double* colweights);
 /* Frees the resident factors and weights (end of RunHeuristic). */
 int ipxgpu_maxvol_release(ipxgpu_ctx* ctx);
 
+/* ---- products with AI outside the KKT solve ---- */
+
+/* ipx::MultiplyAdd on the resident AI = [A I] (reference
+ * src/sparse_matrix.cc:194-209): trans 'N': lhs(m) += alpha * AI * rhs(n+m);
+ * trans 't'/'T': lhs(n+m) += alpha * AI' * rhs(m). Host vectors. These are the
+ * residuals b - AI*x and c - AI'*y of Iterate::ComputeResiduals
+ * (src/iterate.cc:543-551) and the starting point's AI'*y (src/ipm.cc:191).
+ * Every sum is taken in the order of the reference's loops (ScatterColumn over
+ * ascending columns / DotColumn from zero, src/sparse_matrix.h:136-152) with
+ * products and additions rounded separately: the result is bit-identical to
+ * the reference's. Unsharded contexts. */
+int ipxgpu_multiply_add(ipxgpu_ctx* ctx, const double* rhs, double alpha,
+                        double* lhs, char trans);
+
 /* ---- measurement helpers ---- */
 
 /* Runs `reps` device-resident normal-matrix applies on resident vectors and

@@ -28,6 +28,10 @@ REPLACED = ["normal_matrix", "diagonal_precond", "conjugate_residuals", "splitte
             "kkt_solver_diag", "kkt_solver_basis", "maxvolume"]
 ABSENT = ["basiclu_wrapper", "basiclu_kernel"]  # need the un-vendored BASICLU
 SHIMS = ["lu_provider", "sparse_lu", "lapack_min"]
+# Reference translation units compiled unchanged but with one free function renamed, so that
+# the drop-in build can put its own definition in front of it (multiply_add_gpu.cc).
+RENAMED = {"sparse_matrix": ["-DMultiplyAdd=MultiplyAdd_reference"]}
+EXTRA_HOST = ["multiply_add_gpu"]
 
 
 def _newer(target, sources):
@@ -93,16 +97,21 @@ def build_libipx_gpu(force=False):
         stem = f[:-3]
         if stem in REPLACED or stem in ABSENT:
             continue
-        jobs.append((os.path.join(REF, "src", f), os.path.join(OUT, "obj", "ref_" + stem + ".o")))
-    for stem in SHIMS + [r + "_gpu" for r in REPLACED] + ["gpu_bridge"]:
-        jobs.append((os.path.join(HOST, stem + ".cc"), os.path.join(OUT, "obj", stem + ".o")))
+        if stem in RENAMED:
+            jobs.append((os.path.join(REF, "src", f),
+                         os.path.join(OUT, "obj", "ref_" + stem + "_renamed.o"), RENAMED[stem]))
+        else:
+            jobs.append((os.path.join(REF, "src", f),
+                         os.path.join(OUT, "obj", "ref_" + stem + ".o"), []))
+    for stem in SHIMS + [r + "_gpu" for r in REPLACED] + EXTRA_HOST + ["gpu_bridge"]:
+        jobs.append((os.path.join(HOST, stem + ".cc"), os.path.join(OUT, "obj", stem + ".o"), []))
     headers = [os.path.join(HOST, h) for h in os.listdir(HOST) if h.endswith(".h")]
     headers.append(os.path.join(REPO, "include", "ipxgpu.h"))
     procs = []
-    for src, obj in jobs:
+    for src, obj, extra in jobs:
         objs.append(obj)
         if force or _newer(obj, [src] + headers):
-            procs.append((src, subprocess.Popen([CXX] + flags + ["-c", src, "-o", obj],
+            procs.append((src, subprocess.Popen([CXX] + flags + extra + ["-c", src, "-o", obj],
                                                 stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                                                 text=True)))
             if len(procs) >= 8:

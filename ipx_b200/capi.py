@@ -50,7 +50,8 @@ EXPORTS = ("ipxgpu_default_options ipxgpu_last_error ipxgpu_device_count ipxgpu_
            "ipxgpu_kktdiag_solve ipxgpu_lu_load ipxgpu_tri_solve ipxgpu_split_prepare "
            "ipxgpu_split_apply ipxgpu_kktbasis_prepare ipxgpu_basis_solve ipxgpu_kktbasis_solve ipxgpu_time_normal_apply ipxgpu_launch_count ipxgpu_band_selftest ipxgpu_peer_export ipxgpu_peer_import "
            "ipxgpu_maxvol_weights ipxgpu_maxvol_skip ipxgpu_maxvol_update ipxgpu_maxvol_get "
-           "ipxgpu_maxvol_release ipxgpu_set_option ipxgpu_time_tri_solve ipxgpu_tri_trace").split()
+           "ipxgpu_maxvol_release ipxgpu_set_option ipxgpu_time_tri_solve ipxgpu_tri_trace "
+           "ipxgpu_multiply_add").split()
 
 _lib = None
 
@@ -336,6 +337,14 @@ class Context:
 
     def set_option(self, name, value):
         _check(self.lib.ipxgpu_set_option(self.h, name.encode(), i64(value)))
+
+    # ---- products with AI outside the KKT solve ----
+    def multiply_add(self, rhs, alpha, lhs, trans):
+        """lhs + alpha*AI*rhs ('N') or lhs + alpha*AI'*rhs ('T'), summed in the reference's order."""
+        rhs, lhs = _f64(rhs), _f64(lhs).copy()
+        _check(self.lib.ipxgpu_multiply_add(self.h, _d(rhs), C.c_double(alpha), _d(lhs),
+                                            C.c_char(trans.encode())))
+        return lhs
 
     # ---- Maxvolume column sweeps ----
     def maxvol_weights(self, colscale, work):

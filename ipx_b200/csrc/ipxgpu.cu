@@ -19,6 +19,7 @@
 #include "band_plan.cuh"
 #include "pcr_fused.cuh"
 #include "maxvol.cuh"
+#include "madd.cuh"
 
 namespace ipxgpu {
 
@@ -2232,3 +2233,4 @@ int ipxgpu_time_normal_apply(ipxgpu_ctx* c, int reps, int flush_l2, double out_m
 
 #include "split_api.inc"
 #include "maxvol_api.inc"
+#include "madd_api.inc"

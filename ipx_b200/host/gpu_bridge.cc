@@ -20,6 +20,7 @@ struct ModelEntry {
     const double* values = nullptr;
     ipx::Int entries = 0, rows = 0, cols = 0;
     unsigned long long fingerprint = 0;
+    unsigned long long light_fingerprint = 0;  // 256 samples: checked on every MultiplyAdd
     const double* hint_W = nullptr;
     bool hint_weights = false, hint_diag = false;
 };
@@ -46,14 +47,14 @@ Tables& tables() {
 
 // Content fingerprint over a strided sample of AI (<= 64k entries): guards
 // against a new Model whose arrays were allocated at a recycled address.
-unsigned long long Fingerprint(const ipx::SparseMatrix& AI) {
+unsigned long long Fingerprint(const ipx::SparseMatrix& AI, ipx::Int samples = 65536) {
     unsigned long long h = 1469598103934665603ull;
     auto mix = [&](unsigned long long v) {
         h ^= v;
         h *= 1099511628211ull;
     };
     const ipx::Int nz = AI.entries(), nc = AI.cols();
-    const ipx::Int step = nz > 65536 ? nz / 65536 : 1;
+    const ipx::Int step = nz > samples ? nz / samples : 1;
     for (ipx::Int p = 0; p < nz; p += step) {
         unsigned long long bits;
         const double v = AI.value(p);
@@ -62,7 +63,7 @@ unsigned long long Fingerprint(const ipx::SparseMatrix& AI) {
         mix(bits);
         mix((unsigned long long)AI.index(p));
     }
-    const ipx::Int cstep = nc > 65536 ? nc / 65536 : 1;
+    const ipx::Int cstep = nc > samples ? nc / samples : 1;
     for (ipx::Int j = 0; j <= nc; j += cstep) mix((unsigned long long)AI.colptr()[j]);
     return h;
 }
@@ -143,6 +144,7 @@ ContextRef ContextFor(const ipx::Model& model) {
     e.rows = model.rows();
     e.cols = model.cols();
     e.fingerprint = fp;
+    e.light_fingerprint = Fingerprint(AI, 256);
     return ContextRef{e.ctx, e.generation};
 }
 
@@ -153,6 +155,22 @@ ContextRef CurrentContext(const ipx::Model& model) {
     if (it == t.models.end() || !it->second.ctx) return ContextRef{};
     it->second.last_use = ++t.clock;
     return ContextRef{it->second.ctx, it->second.generation};
+}
+
+ipxgpu_ctx* ContextOfMatrix(const ipx::SparseMatrix& A) {
+    Tables& t = tables();
+    std::lock_guard<std::mutex> lock(t.mutex);
+    for (auto& kv : t.models) {
+        ModelEntry& e = kv.second;
+        // AI has rows + cols columns (structural + slack)
+        if (!e.ctx || e.values != A.values() || e.entries != A.entries() || e.rows != A.rows() ||
+            e.rows + e.cols != A.cols())
+            continue;
+        if (e.light_fingerprint != Fingerprint(A, 256)) return nullptr;  // recycled address, other content
+        e.last_use = ++t.clock;
+        return e.ctx;
+    }
+    return nullptr;
 }
 
 int GroupSize() {
@@ -198,6 +216,7 @@ ContextRef GroupContextFor(const ipx::Model& model) {
     e.rows = model.rows();
     e.cols = model.cols();
     e.fingerprint = fp;
+    e.light_fingerprint = Fingerprint(AI, 256);
     return ContextRef{e.ctx, e.generation};
 }
 

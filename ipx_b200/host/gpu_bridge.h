@@ -33,6 +33,11 @@ ContextRef ContextFor(const ipx::Model& model);
 // Cheap lookup by address only; {nullptr, 0} if there is no context.
 ContextRef CurrentContext(const ipx::Model& model);
 
+// The single-GPU context whose model's AI is exactly this matrix object's data (same arrays, same
+// dimensions, same content fingerprint), or nullptr: ipx::MultiplyAdd's way from a SparseMatrix
+// back to the device copy (multiply_add_gpu.cc). Never creates a context.
+ipxgpu_ctx* ContextOfMatrix(const ipx::SparseMatrix& A);
+
 // Several GPUs behind LpSolver: with IPXGPU_NGPUS = G > 1 in the environment KKTSolverDiag
 // runs on a group of G column-sharded contexts of this process (ipxgpu_create_group: one host
 // thread per GPU for the duration of a call, NVLink peer exchange inside the CR kernels), the

@@ -140,6 +140,18 @@ void ipxh_get_model_vectors(void* self, double* b, double* c, double* lb,
     if (ub) FromVector(model.ub(), ub);
 }
 
+// ipx::MultiplyAdd on the model's AI (src/sparse_matrix.cc:194-209): trans 'N'
+// lhs(m) += alpha*AI*rhs(n+m), 'T' lhs(n+m) += alpha*AI'*rhs(m).
+void ipxh_multiply_add_AI(void* self, const double* rhs, double alpha,
+                          double* lhs, char trans) {
+    const Model& model = static_cast<Harness*>(self)->model;
+    const Int m = model.rows(), nm = model.rows() + model.cols();
+    const bool t = trans == 't' || trans == 'T';
+    Vector r = ToVector(rhs, t ? m : nm), l = ToVector(lhs, t ? nm : m);
+    MultiplyAdd(model.AI(), r, alpha, l, trans);
+    FromVector(l, lhs);
+}
+
 // ---- NormalMatrix (src/normal_matrix.h) ----
 
 void ipxh_normal_prepare(void* self, const double* W) {

@@ -107,6 +107,21 @@ void orc_add_normal_product(oint nrow, oint ncol, const oint* Ap,
     }
 }
 
+/* ---- MultiplyAdd, src/sparse_matrix.cc:194-209 ---- */
+
+void orc_multiply_add(oint nrow, oint ncol, const oint* Ap, const oint* Ai,
+                      const double* Ax, const double* rhs, double alpha,
+                      double* lhs, char trans) {
+    (void)nrow;
+    if (trans == 't' || trans == 'T') {
+        for (oint j = 0; j < ncol; j++)                              /* :201-202 */
+            lhs[j] += alpha * dot_column(Ap, Ai, Ax, j, rhs);
+    } else {
+        for (oint j = 0; j < ncol; j++)                              /* :206-207 */
+            scatter_column(Ap, Ai, Ax, j, alpha * rhs[j], lhs);
+    }
+}
+
 /* ---- TriangularSolve, src/sparse_matrix.cc:224-301 ---- */
 
 oint orc_triangular_solve(oint ncol, const oint* Ap, const oint* Ai,

@@ -57,6 +57,13 @@ void orc_add_normal_product(oint nrow, oint ncol, const oint* Ap,
                             const oint* Ai, const double* Ax, const double* D,
                             const double* rhs, double* lhs);
 
+/* ipx::MultiplyAdd (src/sparse_matrix.cc:194-209): trans 'N' lhs(nrow) +=
+ * alpha*A*rhs(ncol), 't'/'T' lhs(ncol) += alpha*A'*rhs(nrow); the reference's
+ * loops, so the sums are taken in the reference's order. */
+void orc_multiply_add(oint nrow, oint ncol, const oint* Ap, const oint* Ai,
+                      const double* Ax, const double* rhs, double alpha,
+                      double* lhs, char trans);
+
 /* In-place sparse triangular solve; returns nnz(x).
  * trans: 't'/'T' transposed. uplo: 'u'/'U' upper else lower. unitdiag != 0:
  * unit diagonal not stored; otherwise the diagonal is the LAST entry of each

@@ -126,6 +126,13 @@ class IpxModel:
         return b, c, lb, ub
 
     # NormalMatrix
+    def multiply_add_AI(self, rhs, alpha, lhs, trans):
+        """ipx::MultiplyAdd(model.AI(), rhs, alpha, lhs, trans); returns the updated lhs."""
+        rhs, lhs = _f64(rhs), _f64(lhs).copy()
+        self.lib.ipxh_multiply_add_AI(self.h, _d(rhs), C.c_double(alpha), _d(lhs),
+                                      C.c_char(trans.encode()))
+        return lhs
+
     def normal_prepare(self, W):
         W = _f64(W)
         self.lib.ipxh_normal_prepare(self.h, _d(W))

@@ -102,6 +102,14 @@ def add_normal_product(nrow, ncol, A, D, rhs, lhs):
     return lhs
 
 
+def multiply_add(nrow, ncol, A, rhs, alpha, lhs, trans):
+    """ipx::MultiplyAdd (reference src/sparse_matrix.cc:194-209); returns the updated lhs."""
+    rhs, lhs = _f64(rhs), _f64(lhs).copy()
+    lib().orc_multiply_add(oint(nrow), oint(ncol), *A.args, _d(rhs), C.c_double(alpha), _d(lhs),
+                           C.c_char(trans.encode()))
+    return lhs
+
+
 def triangular_solve(dim, A, x, trans, uplo, unitdiag):
     x = _f64(x).copy()
     nz = lib().orc_triangular_solve(oint(dim), *A.args, _d(x), C.c_char(trans.encode()),

@@ -168,6 +168,14 @@ def test_oracle_equals_reference_bitwise(oracle, reflib, shape):
         y1, i1 = oracle.pcr_solve(oracle.normal_operator(m, n, A, W), m, diag, rhs, tol, resscale, -1)
         assert i0["iter"] == i1["iter"] and i0["errflag"] == i1["errflag"]
         assert np.array_equal(y0, y1)
+    # MultiplyAdd on AI (src/sparse_matrix.cc:194-209), both directions
+    for alpha in (-1.0, 0.37):
+        xx, ll = rng.standard_normal(n + m), rng.standard_normal(m)
+        assert (mdl.multiply_add_AI(xx, alpha, ll, "N").tobytes()
+                == oracle.multiply_add(m, n + m, A, xx, alpha, ll, "N").tobytes())
+        yy, ll = rng.standard_normal(m), rng.standard_normal(n + m)
+        assert (mdl.multiply_add_AI(yy, alpha, ll, "T").tobytes()
+                == oracle.multiply_add(m, n + m, A, yy, alpha, ll, "T").tobytes())
     # iteration limit and nonzero start
     y0, i0 = mdl.pcr_solve(rhs, 0.0, None, 4, lhs0=0.5 * rhs)
     y1, i1 = oracle.pcr_solve(oracle.normal_operator(m, n, A, W), m, diag, rhs, 0.0, None, 4,
