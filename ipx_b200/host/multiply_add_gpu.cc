@@ -26,7 +26,8 @@ void MultiplyAdd_reference(const SparseMatrix& A, const Vector& rhs, double alph
                            char trans);
 
 void MultiplyAdd(const SparseMatrix& A, const Vector& rhs, double alpha, Vector& lhs, char trans) {
-    ipxgpu_ctx* ctx = ipxb200::ContextOfMatrix(A);
+    // an empty side (no rows, or no columns at all) leaves nothing to do on the device
+    ipxgpu_ctx* ctx = rhs.size() == 0 || lhs.size() == 0 ? nullptr : ipxb200::ContextOfMatrix(A);
     if (!ctx) {
         MultiplyAdd_reference(A, rhs, alpha, lhs, trans);
         return;
@@ -40,7 +41,6 @@ void MultiplyAdd(const SparseMatrix& A, const Vector& rhs, double alpha, Vector&
         assert((Int)rhs.size() == n);
         assert((Int)lhs.size() == m);
     }
-    if (m == 0 || n == 0) return;
     ipxb200::Check(ipxgpu_multiply_add(ctx, &rhs[0], alpha, &lhs[0], trans));
 }
 
