@@ -182,3 +182,19 @@ def test_oracle_equals_reference_bitwise(oracle, reflib, shape):
                               lhs0=0.5 * rhs)
     assert i0["errflag"] == i1["errflag"] == 201 and np.array_equal(y0, y1)
     mdl.close()
+
+
+def test_dropin_multiply_add_without_a_context_is_the_reference(reflib, gpulib):
+    """ipx::MultiplyAdd of the drop-in build (ipx_b200/host/multiply_add_gpu.cc) for a matrix
+    that is not resident on a device - here: a model nobody has factorized yet, no GPU needed -
+    is the reference's own function under its compile-time name: same bits."""
+    lp = lpgen.random_sparse_lp(120, 900, 6, 77)
+    ref, gpu = reflib.model(lp), gpulib.model(lp)
+    m, n = ref.m, ref.n
+    rng = np.random.default_rng(78)
+    x, lm = rng.standard_normal(n + m), rng.standard_normal(m)
+    y, ln = rng.standard_normal(m), rng.standard_normal(n + m)
+    assert gpu.multiply_add_AI(x, -1.0, lm, "N").tobytes() == ref.multiply_add_AI(x, -1.0, lm, "N").tobytes()
+    assert gpu.multiply_add_AI(y, 0.5, ln, "T").tobytes() == ref.multiply_add_AI(y, 0.5, ln, "T").tobytes()
+    ref.close()
+    gpu.close()
