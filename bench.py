@@ -53,7 +53,7 @@ M_ROWS = 100_000
 N_COLS = 1_000_000
 NNZ_PER_COL = 10
 SEED = 1002
-NCU_TRAFFIC_BYTES_PER_APPLY = 297_520_000  # see roofline.traffic below
+NCU_TRAFFIC_BYTES_PER_APPLY = 296_715_000  # see roofline.traffic below
 
 
 def algorithmic_bytes(m, n, nnzA):
@@ -552,11 +552,11 @@ def run_gpu(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak,
                          # dram__bytes_read+write of one pcr_fused_kernel launch (a CR solve of
-                         # 6 iterations = 7 applies: 2051.9 MB read + 30.7 MB written) / 7, from
-                         # the ncu --set full capture profiles/r01b_ncu_full_band_fused.csv;
+                         # 6 iterations = 7 applies: 2052.27 MB read + 24.74 MB written) / 7, from
+                         # the ncu --set full capture profiles/r02_ncu_full_band_fused.csv;
                          # only valid for the 1-GPU C2 workload.
                          "traffic": NCU_TRAFFIC_BYTES_PER_APPLY if world == 1 and not STRONG else None,
-                         "traffic_source": "profiles/r01b_ncu_full_band_fused.csv",
+                         "traffic_source": "profiles/r02_ncu_full_band_fused.csv",
                          "peak_source": peak_src,
                          "kernel": kernel_name,
                          "algorithmic_bytes_per_apply": bytes_apply,
